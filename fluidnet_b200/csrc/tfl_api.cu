@@ -1,0 +1,740 @@
+// C ABI of libtfl (include/tfl.h): context, scratch arena, argument checks that mirror the
+// asserts of the reference's Lua wrappers (torch/tfluids/init.lua), and the operator /
+// whole-step entry points that enqueue the kernels of tfl_stencils.cu, tfl_model_stages.cu
+// and tfl_cnn*.cu on the context's stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "tfl_kernels.h"
+
+using namespace tfl;
+
+struct tfl_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t arena_used = 0;
+  unsigned long long* counters = nullptr;   // [0] trace faults, [1] bad occupancy cells
+  double* dscratch = nullptr;               // small double scratch (reductions), 256 entries
+  long long launches = 0;
+  bool slab = false;
+  int zoff = 0, gnz = 0, zlo = 0, zhi = 0;
+};
+
+struct tfl_cnn {
+  int is3d = 1;
+  int n_layers = 0;
+  std::vector<int> cin, cout, ks;
+  std::vector<float*> w;     // device, [cin][tap][cout]
+  std::vector<float*> b;     // device, [cout]
+  int max_c = 0;
+};
+
+namespace {
+
+int fail(tfl_ctx* ctx, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return 1;
+}
+
+#define TFL_CUDA(ctx, call)                                                            \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) return fail(ctx, "%s: %s", #call, cudaGetErrorString(e_));  \
+  } while (0)
+
+int check_launch(tfl_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// Bump allocator over one growing device buffer (the reference's getTempStorage,
+// tfluids/init.lua:35-64).  Growing synchronises; steady state does not allocate.
+int arena_reserve(tfl_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->arena_bytes) return 0;
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  ctx->arena_bytes = 0;
+  void* p = nullptr;
+  TFL_CUDA(ctx, cudaMalloc(&p, bytes));
+  ctx->arena = (char*)p;
+  ctx->arena_bytes = bytes;
+  return 0;
+}
+struct Carver {
+  tfl_ctx* ctx;
+  size_t off = 0;
+  explicit Carver(tfl_ctx* c) : ctx(c) {}
+  template <typename T>
+  T* take(size_t count) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    off = a + count * sizeof(T);
+    return (T*)(ctx->arena + a);
+  }
+};
+size_t carve_bytes(std::initializer_list<size_t> sizes) {
+  size_t off = 0;
+  for (size_t s : sizes) off = ((off + 255) & ~(size_t)255) + s;
+  return off + 256;
+}
+
+bool same_spatial(const tfl_grid* a, const tfl_grid* b) {
+  return a->nb == b->nb && a->nz == b->nz && a->ny == b->ny && a->nx == b->nx;
+}
+
+// Mirrors the shape asserts of init.lua (e.g. :100-120, :177-191).
+int check_scalar(tfl_ctx* ctx, const tfl_grid* g, const char* name) {
+  if (!g || !g->data) return fail(ctx, "%s is nil", name);
+  if (g->nc != 1) return fail(ctx, "%s is not scalar", name);
+  if (g->nb < 1 || g->nz < 1 || g->ny < 1 || g->nx < 1) return fail(ctx, "%s: Dimension mismatch", name);
+  return 0;
+}
+int check_vel(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags) {
+  if (!U || !U->data) return fail(ctx, "U is nil");
+  if (U->nc != 2 && U->nc != 3) return fail(ctx, "2D velocity field must have only 2 channels");
+  if (U->nc == 2 && flags->nz != 1) return fail(ctx, "2D velocity field but zdepth > 1");
+  if (!same_spatial(U, flags)) return fail(ctx, "Size mismatch");
+  return 0;
+}
+
+int make_geo(tfl_ctx* ctx, const tfl_grid* flags, int is3d, Geo* g) {
+  g->nx = flags->nx; g->ny = flags->ny; g->nz = flags->nz; g->nb = flags->nb;
+  g->is3d = is3d ? 1 : 0;
+  g->nc = is3d ? 3 : 2;
+  g->n = (long long)flags->nx * flags->ny * flags->nz;
+  g->faults = ctx->counters;
+  if (ctx->slab) {
+    if (!is3d) return fail(ctx, "slab decomposition needs a 3D grid");
+    g->zoff = ctx->zoff; g->gnz = ctx->gnz; g->zlo = ctx->zlo; g->zhi = ctx->zhi;
+    if (g->zlo < 0 || g->zhi > g->nz || g->zlo >= g->zhi || g->zoff < 0 || g->zoff + g->nz > g->gnz)
+      return fail(ctx, "slab range does not fit the local grid");
+  } else {
+    g->zoff = 0; g->gnz = flags->nz; g->zlo = 0; g->zhi = flags->nz;
+  }
+  if (!is3d && flags->nz != 1) return fail(ctx, "2D grid must have zsize == 1");
+  if (g->n * (long long)g->nb * 3 >= (1LL << 31) * 4) return fail(ctx, "grid too large");
+  return 0;
+}
+
+float get_dx(const Geo& g) {     // third_party/grid.cc:37-40 on the GLOBAL grid
+  int m = g.nx > g.ny ? g.nx : g.ny;
+  if (g.gnz > m) m = g.gnz;
+  return 1.0f / (float)m;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tfl_version(void) { return "libtfl 0.1 (sm_100a)"; }
+
+int tfl_advect_method_from_string(const char* s) {
+  if (!s) return -1;
+  if (!strcmp(s, "euler")) return TFL_ADVECT_EULER;
+  if (!strcmp(s, "maccormack")) return TFL_ADVECT_MACCORMACK;
+  if (!strcmp(s, "eulerOurs")) return TFL_ADVECT_EULER_OURS;
+  if (!strcmp(s, "rk2Ours")) return TFL_ADVECT_RK2_OURS;
+  if (!strcmp(s, "rk3Ours")) return TFL_ADVECT_RK3_OURS;
+  if (!strcmp(s, "maccormackOurs")) return TFL_ADVECT_MACCORMACK_OURS;
+  return -1;
+}
+
+int tfl_create(tfl_ctx** out, int device) {
+  if (!out) return 1;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  tfl_ctx* c = new tfl_ctx();
+  c->device = device;
+  if (cudaStreamCreate(&c->stream) != cudaSuccess) { delete c; return 1; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, 16 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return 1; }
+  c->counters = (unsigned long long*)p;
+  cudaMemset(c->counters, 0, 16 * sizeof(unsigned long long));
+  if (cudaMalloc(&p, 256 * sizeof(double)) != cudaSuccess) { delete c; return 1; }
+  c->dscratch = (double*)p;
+  *out = c;
+  return 0;
+}
+
+void tfl_destroy(tfl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->dscratch) cudaFree(ctx->dscratch);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* tfl_last_error(const tfl_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int tfl_set_stream(tfl_ctx* ctx, void* s) {
+  if (!ctx) return 1;
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (s == nullptr) {
+    if (!ctx->own_stream) {
+      TFL_CUDA(ctx, cudaStreamCreate(&ctx->stream));
+      ctx->own_stream = true;
+    }
+    return 0;
+  }
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  return 0;
+}
+void* tfl_get_stream(tfl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int tfl_sync(tfl_ctx* ctx) {
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int64_t tfl_launch_count(const tfl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset) {
+  unsigned long long v = 0;
+  TFL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (count) *count = (int64_t)v;
+  if (reset) TFL_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(v), ctx->stream));
+  return 0;
+}
+
+int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo, int32_t z_hi) {
+  if (global_nz <= 0) { ctx->slab = false; return 0; }
+  ctx->slab = true;
+  ctx->zoff = z_offset; ctx->gnz = global_nz; ctx->zlo = z_lo; ctx->zhi = z_hi;
+  return 0;
+}
+
+int tfl_alloc(tfl_ctx* ctx, size_t bytes, void** p) {
+  TFL_CUDA(ctx, cudaMalloc(p, bytes));
+  return 0;
+}
+int tfl_free(tfl_ctx* ctx, void* p) {
+  TFL_CUDA(ctx, cudaFree(p));
+  return 0;
+}
+int tfl_alloc_host(tfl_ctx* ctx, size_t bytes, void** p) {
+  TFL_CUDA(ctx, cudaMallocHost(p, bytes));
+  return 0;
+}
+int tfl_free_host(tfl_ctx* ctx, void* p) {
+  TFL_CUDA(ctx, cudaFreeHost(p));
+  return 0;
+}
+int tfl_memcpy_h2d(tfl_ctx* ctx, void* d, const void* h, size_t bytes) {
+  TFL_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int tfl_memcpy_d2h(tfl_ctx* ctx, void* h, const void* d, size_t bytes) {
+  TFL_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+int tfl_memcpy_d2d(tfl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  TFL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Operators
+// ---------------------------------------------------------------------------------------
+int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd) {
+  if (check_scalar(ctx, flags, "flags")) return 1;
+  if (!((!is_3d || (ctx->slab ? ctx->gnz : flags->nz) >= bnd * 2 + 1) && flags->ny >= bnd * 2 + 1 &&
+        flags->nx >= bnd * 2 + 1))
+    return fail(ctx, "simulation domain not big enough!");       // init.lua:549-551
+  Geo g;
+  if (make_geo(ctx, flags, is_3d, &g)) return 1;
+  launch_empty_domain(flags->data, g, bnd, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "emptyDomain");
+}
+
+int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* occ, int64_t* bad) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, occ, "occupancy")) return 1;
+  if (!same_spatial(flags, occ)) return fail(ctx, "Size mismatch");
+  const long long n = (long long)flags->nb * flags->nz * flags->ny * flags->nx;
+  TFL_CUDA(ctx, cudaMemsetAsync(ctx->counters + 1, 0, sizeof(unsigned long long), ctx->stream));
+  launch_flags_to_occupancy(flags->data, occ->data, n, ctx->counters + 1, ctx->stream);
+  ctx->launches += 1;
+  if (check_launch(ctx, "flagsToOccupancy")) return 1;
+  if (bad) {
+    unsigned long long v = 0;
+    TFL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->counters + 1, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *bad = (int64_t)v;
+  }
+  return 0;
+}
+
+int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  launch_set_wall_bcs(U->data, flags->data, g, 0, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "setWallBcsForward");
+}
+
+int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                                    const tfl_grid* div) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, div, "UDiv")) return 1;
+  if (!same_spatial(flags, div)) return fail(ctx, "Size mismatch");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  launch_divergence(U->data, flags->data, div->data, g, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "velocityDivergenceForward");
+}
+
+int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p")) return 1;
+  if (!same_spatial(flags, p)) return fail(ctx, "Size mismatch");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  launch_velocity_update(U->data, flags->data, p->data, g, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "velocityUpdateForward");
+}
+
+int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* density,
+                     const float gravity[3], float dt) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, density, "density"))
+    return 1;
+  if (!same_spatial(flags, density)) return fail(ctx, "Size mismatch");
+  if (!gravity) return fail(ctx, "gravity must be a 3D vector (even in 2D).");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  // strength = (-g) * (dt / dx), third_party/tfluids.cc:1190-1191.
+  const float scale = dt / get_dx(g);
+  const float s[3] = {(-gravity[0]) * scale, (-gravity[1]) * scale, (-gravity[2]) * scale};
+  launch_add_buoyancy(U->data, flags->data, density->data, s, g, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "addBuoyancy");
+}
+
+int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const float gravity[3], float dt) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
+  if (!gravity) return fail(ctx, "gravity must be a 3D vector (even in 2D).");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  const float scale = dt / get_dx(g);                 // third_party/tfluids.cc:1259-1260
+  const float f[3] = {gravity[0] * scale, gravity[1] * scale, gravity[2] * scale};
+  launch_add_gravity(U->data, flags->data, f, g, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "addGravity");
+}
+
+int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, float strength) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  if (arena_reserve(ctx, carve_bytes({cells * 3 * 4, cells * 4}))) return 1;
+  Carver cv(ctx);
+  float* curl = cv.take<float>(cells * 3);
+  float* cnorm = cv.take<float>(cells);
+  ctx->launches += launch_vorticity(U->data, flags->data, strength, curl, cnorm, g, ctx->stream);
+  return check_launch(ctx, "vorticityConfinement");
+}
+
+int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid* U, const tfl_grid* flags,
+                      int method, int sample_outside_fluid, float strength, const tfl_grid* s_dst) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, s, "s") || check_vel(ctx, U, flags)) return 1;
+  if (!same_spatial(flags, s)) return fail(ctx, "Size mismatch");
+  if (s_dst && (check_scalar(ctx, s_dst, "sDst") || !same_spatial(s_dst, s))) return fail(ctx, "Size mismatch");
+  if (method < 0 || method > 5)
+    return fail(ctx, "advection method not supported (options are: euler, maccormack, rk2Ours, rk3Ours, "
+                     "eulerOurs, maccormackOurs)");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  const bool in_place = (s_dst == nullptr) || (s_dst->data == s->data);
+  if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4}))) return 1;
+  Carver cv(ctx);
+  float* fwd = cv.take<float>(cells);
+  float* fwd_pos = cv.take<float>(cells * g.nc);
+  float* tmp = cv.take<float>(cells);
+  float* dst = in_place ? tmp : s_dst->data;
+  Geo gf = g;     // forward pass over every local plane (its halo planes feed the backward pass)
+  gf.zlo = 0; gf.zhi = g.nz;
+  const int nl = launch_advect_scalar(dt, s->data, U->data, flags->data, method, sample_outside_fluid,
+                                      strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
+  if (nl < 0) return fail(ctx, "advectScalar: bad method");
+  ctx->launches += nl;
+  if (check_launch(ctx, "advectScalar")) return 1;
+  if (in_place) {
+    // s:copy(tmp) (init.lua:145-148); only the computed planes in slab mode.
+    for (int b = 0; b < g.nb; b++) {
+      const size_t off = (size_t)b * g.n + (size_t)g.zlo * g.ny * g.nx;
+      const size_t cnt = (size_t)(g.zhi - g.zlo) * g.ny * g.nx;
+      TFL_CUDA(ctx, cudaMemcpyAsync(s->data + off, tmp + off, cnt * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  return 0;
+}
+
+int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* flags, int method,
+                   float strength, const tfl_grid* U_dst) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
+  if (U_dst && (check_vel(ctx, U_dst, flags) || U_dst->nc != U->nc)) return fail(ctx, "Size mismatch");
+  if (method < 0 || method > 5) return fail(ctx, "advection method not supported");
+  Geo g;
+  if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  const bool in_place = (U_dst == nullptr) || (U_dst->data == U->data);
+  if (arena_reserve(ctx, carve_bytes({cells * 4 * g.nc, cells * 4 * g.nc}))) return 1;
+  Carver cv(ctx);
+  float* fwd = cv.take<float>(cells * g.nc);
+  float* tmp = cv.take<float>(cells * g.nc);
+  float* dst = in_place ? tmp : U_dst->data;
+  Geo gf = g;
+  gf.zlo = 0; gf.zhi = g.nz;
+  if (ctx->slab) {     // the MAC samples reach one plane below: never start a trace on local plane 0 / nz-1
+    gf.zlo = 1; gf.zhi = g.nz - 1;
+    if (g.zoff == 0) gf.zlo = 0;
+    if (g.zoff + g.nz == g.gnz) gf.zhi = g.nz;
+  }
+  const int nl = launch_advect_vel(dt, U->data, flags->data, method, strength, dst, fwd, g, gf, ctx->stream);
+  if (nl < 0) return fail(ctx, "advectVel: bad method");
+  ctx->launches += nl;
+  if (check_launch(ctx, "advectVel")) return 1;
+  if (in_place) {
+    for (int b = 0; b < g.nb; b++)
+      for (int c = 0; c < g.nc; c++) {
+        const size_t off = ((size_t)b * g.nc + c) * g.n + (size_t)g.zlo * g.ny * g.nx;
+        const size_t cnt = (size_t)(g.zhi - g.zlo) * g.ny * g.nx;
+        TFL_CUDA(ctx, cudaMemcpyAsync(U->data + off, tmp + off, cnt * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+  }
+  return 0;
+}
+
+int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
+                                   const tfl_grid* div, int is_3d, float p_tol, int max_iter,
+                                   float* residual, int* iterations) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
+  if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
+  if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
+  if (max_iter < 1) return fail(ctx, "At least 1 iteration is needed (maxIter < 1)");
+  if (ctx->slab) return fail(ctx, "Jacobi on a z-slab goes through the multi-GPU driver (halo exchange per sweep)");
+  Geo g;
+  if (make_geo(ctx, flags, is_3d, &g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  if (arena_reserve(ctx, carve_bytes({cells * 4, cells}))) return 1;
+  Carver cv(ctx);
+  float* p_prev = cv.take<float>(cells);
+  unsigned char* mask = cv.take<unsigned char>(cells);
+  cudaStream_t st = ctx->stream;
+  launch_jacobi_mask(flags->data, mask, g, st);
+  ctx->launches += 1;
+  // p <- 0, pPrev <- 0 (generic/tfluids.cu:1854-1855).
+  TFL_CUDA(ctx, cudaMemsetAsync(p->data, 0, cells * 4, st));
+  TFL_CUDA(ctx, cudaMemsetAsync(p_prev, 0, cells * 4, st));
+  float* cur = p->data;
+  float* prev = p_prev;
+  float res = 0.0f;
+  int iter = 0;
+  const bool need_every = p_tol > 0.0f;     // residual < pTol can only trigger for pTol > 0
+  std::vector<double> h(g.nb);
+  for (;;) {
+    launch_jacobi_iter(mask, div->data, prev, cur, g, st);
+    ctx->launches += 1;
+    const bool last = (iter + 1 >= max_iter);
+    if (need_every || (last && residual)) {
+      TFL_CUDA(ctx, cudaMemsetAsync(ctx->dscratch, 0, sizeof(double) * g.nb, st));
+      launch_sqdiff(p->data, p_prev, g.n, g.nb, ctx->dscratch, st);
+      ctx->launches += 1;
+      TFL_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->dscratch, sizeof(double) * g.nb, cudaMemcpyDeviceToHost, st));
+      TFL_CUDA(ctx, cudaStreamSynchronize(st));
+      double worst = 0.0;
+      for (int b = 0; b < g.nb; b++) { const double nr = sqrt(h[b]); if (nr > worst) worst = nr; }
+      res = (float)worst;
+      if (res < p_tol) break;
+    }
+    iter++;
+    if (iter >= max_iter) break;
+    float* t = cur; cur = prev; prev = t;
+  }
+  if (cur == p_prev) TFL_CUDA(ctx, cudaMemcpyAsync(p->data, p_prev, cells * 4, cudaMemcpyDeviceToDevice, st));
+  if (check_launch(ctx, "solveLinearSystemJacobi")) return 1;
+  if (residual) *residual = res;
+  if (iterations) *iterations = iter;
+  return 0;
+}
+
+int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc) {
+  if (!x || !inv_mask || !bc || !x->data || !inv_mask->data || !bc->data) return fail(ctx, "applyBC: nil tensor");
+  if (!same_spatial(x, inv_mask) || !same_spatial(x, bc) || x->nc != inv_mask->nc || x->nc != bc->nc)
+    return fail(ctx, "Size mismatch");
+  const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
+  launch_apply_bc(x->data, inv_mask->data, bc->data, n, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "applyBC");
+}
+
+int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
+  if (!x || !x->data) return fail(ctx, "clamp: nil tensor");
+  const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
+  launch_clamp(x->data, lo, hi, n, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "clamp");
+}
+
+// ---------------------------------------------------------------------------------------
+// CNN projection
+// ---------------------------------------------------------------------------------------
+int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
+                   const int32_t* ksize, const float* const* weights, const float* const* biases,
+                   tfl_cnn** out) {
+  if (!out || n_layers < 1) return fail(ctx, "cnn: bad arguments");
+  if (cin[0] != 3) return fail(ctx, "cnn: the first layer must take 3 channels (pDiv, div, occupancy)");
+  if (cout[n_layers - 1] != 1) return fail(ctx, "Last layer osize must be 1 (pressure)");   // model.lua:244
+  tfl_cnn* m = new tfl_cnn();
+  m->is3d = is_3d ? 1 : 0;
+  m->n_layers = n_layers;
+  for (int l = 0; l < n_layers; l++) {
+    if (l > 0 && cin[l] != cout[l - 1]) { delete m; return fail(ctx, "cnn: channel mismatch at layer %d", l); }
+    if (ksize[l] % 2 != 1) { delete m; return fail(ctx, "convolution size must be odd"); }   // model_utils.lua:70
+    const int kz = is_3d ? ksize[l] : 1;
+    const int taps = kz * ksize[l] * ksize[l];
+    std::vector<float> relaid((size_t)cin[l] * taps * cout[l]);
+    for (int o = 0; o < cout[l]; o++)
+      for (int c = 0; c < cin[l]; c++)
+        for (int t = 0; t < taps; t++)
+          relaid[((size_t)c * taps + t) * cout[l] + o] = weights[l][((size_t)o * cin[l] + c) * taps + t];
+    float *dw = nullptr, *db = nullptr;
+    if (cudaMalloc((void**)&dw, relaid.size() * 4) != cudaSuccess ||
+        cudaMalloc((void**)&db, cout[l] * 4) != cudaSuccess) { delete m; return fail(ctx, "cnn: cudaMalloc failed"); }
+    cudaMemcpy(dw, relaid.data(), relaid.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, biases[l], cout[l] * 4, cudaMemcpyHostToDevice);
+    m->cin.push_back(cin[l]); m->cout.push_back(cout[l]); m->ks.push_back(ksize[l]);
+    m->w.push_back(dw); m->b.push_back(db);
+    if (cout[l] > m->max_c) m->max_c = cout[l];
+  }
+  *out = m;
+  return 0;
+}
+
+void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
+  if (!m) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (float* p : m->w) cudaFree(p);
+  for (float* p : m->b) cudaFree(p);
+  delete m;
+}
+
+static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const float* U_div,
+                            const float* flags, float* p_out, float* U_out, float threshold, const Geo& g,
+                            char* scratch, float** scale_dev_out) {
+  // scratch layout (caller reserved): U1 [nc], x0 [3], actA [max_c], actB [max_c], scale [nb]
+  const size_t cells = (size_t)g.n * g.nb;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = scratch + off; off = (off + bytes + 255) & ~(size_t)255; return p; };
+  float* U1 = (float*)take(cells * 4 * g.nc);
+  float* x0 = (float*)take(cells * 4 * 3);
+  float* actA = (float*)take(cells * 4 * m->max_c);
+  float* actB = (float*)take(cells * 4 * m->max_c);
+  float* scale = (float*)take(sizeof(float) * g.nb);
+  double* sums = ctx->dscratch + 64;
+  cudaStream_t st = ctx->stream;
+  TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
+  launch_cnn_mask_stats(U_div, flags, U1, sums, g, st);
+  launch_cnn_scale(sums, scale, g.nb, (long long)g.nc * g.n, threshold, st);
+  launch_cnn_inputs(p_div, U1, flags, scale, x0, g, st);
+  ctx->launches += 3;
+  const float* in = x0;
+  float* bufs[2] = {actA, actB};
+  for (int l = 0; l < m->n_layers; l++) {
+    float* o = bufs[l & 1];
+    const int relu = (l < m->n_layers - 1) ? 1 : 0;
+    if (launch_conv_direct(in, o, m->w[l], m->b[l], m->cin[l], m->cout[l], m->ks[l], relu, g, st) < 0)
+      return fail(ctx, "cnn: unsupported layer shape cout=%d k=%d", m->cout[l], m->ks[l]);
+    ctx->launches += 1;
+    in = o;
+  }
+  launch_cnn_finish(in, U1, flags, scale, p_out, U_out, g, st);
+  ctx->launches += 1;
+  if (scale_dev_out) *scale_dev_out = scale;
+  return check_launch(ctx, "cnn_project");
+}
+
+static size_t cnn_scratch_bytes(const tfl_cnn* m, const Geo& g) {
+  const size_t cells = (size_t)g.n * g.nb;
+  return cells * 4 * (g.nc + 3 + 2 * (size_t)m->max_c) + 4 * g.nb + 8 * 256;
+}
+
+int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_grid* U_div,
+                    const tfl_grid* flags, const tfl_grid* p_out, const tfl_grid* U_out, float threshold,
+                    float* scale_out) {
+  if (!m) return fail(ctx, "cnn is nil");
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U_div, flags) ||
+      check_scalar(ctx, p_out, "p") || check_vel(ctx, U_out, flags))
+    return 1;
+  if (!same_spatial(flags, p_div) || !same_spatial(flags, p_out) || U_out->nc != U_div->nc)
+    return fail(ctx, "Size mismatch");
+  if ((U_div->nc == 3) != (m->is3d != 0)) return fail(ctx, "model / data dimensionality mismatch");
+  if (ctx->slab) return fail(ctx, "cnn_project on a z-slab goes through the multi-GPU driver");
+  Geo g;
+  if (make_geo(ctx, flags, m->is3d, &g)) return 1;
+  if (arena_reserve(ctx, cnn_scratch_bytes(m, g))) return 1;
+  float* scale_dev = nullptr;
+  if (cnn_project_impl(ctx, m, p_div->data, U_div->data, flags->data, p_out->data, U_out->data, threshold, g,
+                       ctx->arena, &scale_dev))
+    return 1;
+  if (scale_out) {
+    TFL_CUDA(ctx, cudaMemcpyAsync(scale_out, scale_dev, sizeof(float) * g.nb, cudaMemcpyDeviceToHost, ctx->stream));
+    TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// tfluids.simulate (lib/simulate.lua:175-327)
+// ---------------------------------------------------------------------------------------
+static int set_const_vals(tfl_ctx* ctx, const tfl_state* s) {       // lib/simulate.lua:130-160
+  if (s->p_bc.data && s->p_bc_inv_mask.data && tfl_apply_bc(ctx, &s->p, &s->p_bc_inv_mask, &s->p_bc)) return 1;
+  if (s->U_bc.data && s->U_bc_inv_mask.data && tfl_apply_bc(ctx, &s->U, &s->U_bc_inv_mask, &s->U_bc)) return 1;
+  if (s->density.data && s->density_bc.data && s->density_bc_inv_mask.data &&
+      tfl_apply_bc(ctx, &s->density, &s->density_bc_inv_mask, &s->density_bc))
+    return 1;
+  return 0;
+}
+
+int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl_cnn* cnn) {
+  if (!s || !mc) return fail(ctx, "simulate: nil state / mconf");
+  if (check_scalar(ctx, &s->flags, "flags") || check_scalar(ctx, &s->p, "pDiv") || check_vel(ctx, &s->U, &s->flags))
+    return 1;
+  const int is3d = s->U.nc == 3;
+  Geo g;
+  if (make_geo(ctx, &s->flags, is3d, &g)) return 1;
+  const bool has_density = s->density.data != nullptr;
+  // 1-2. advect scalars then velocity (lib/simulate.lua:183-199).
+  if (has_density && tfl_advect_scalar(ctx, mc->dt, &s->density, &s->U, &s->flags, mc->advection_method, 0,
+                                       mc->maccormack_strength, nullptr))
+    return 1;
+  if (tfl_advect_vel(ctx, mc->dt, &s->U, &s->flags, mc->advection_method, mc->maccormack_strength, nullptr))
+    return 1;
+  if (set_const_vals(ctx, s)) return 1;                               // :202
+  const int dmax = std::max(g.nx, std::max(g.ny, g.gnz));
+  const double dx = 1.0 / (double)dmax;                              // tfluids.getDx, init.lua:560-564
+  // gravity:mul(scalar) is a float tensor op: the Lua double is cast to float first.
+  if (has_density && mc->buoyancy_scale > 0.0) {                     // :216-226
+    const float k = (float)(-(dx / 4.0) * mc->buoyancy_scale);
+    const float gv[3] = {mc->gravity[0] * k, mc->gravity[1] * k, mc->gravity[2] * k};
+    if (tfl_add_buoyancy(ctx, &s->U, &s->flags, &s->density, gv, mc->dt)) return 1;
+  }
+  if (mc->gravity_scale > 0.0) {                                     // :229-233
+    const float k = (float)((-dx / 4.0) * mc->gravity_scale);
+    const float gv[3] = {mc->gravity[0] * k, mc->gravity[1] * k, mc->gravity[2] * k};
+    if (tfl_add_gravity(ctx, &s->U, &s->flags, gv, mc->dt)) return 1;
+  }
+  if (mc->vorticity_confinement_amp > 0.0) {                         // :236-239
+    const float amp = (float)(dx * mc->vorticity_confinement_amp);
+    if (tfl_vorticity_confinement(ctx, &s->U, &s->flags, amp)) return 1;
+  }
+  if (mc->sim_method != TFL_SIM_CONVNET && tfl_set_wall_bcs_forward(ctx, &s->U, &s->flags)) return 1;  // :248-251
+  if (set_const_vals(ctx, s)) return 1;                               // :252
+  if (mc->sim_method == TFL_SIM_CONVNET) {                            // :262-272
+    if (!cnn) return fail(ctx, "simulate: simMethod 'convnet' needs a model");
+    if (tfl_cnn_project(ctx, cnn, &s->p, &s->U, &s->flags, &s->p, &s->U, mc->normalize_input_threshold, nullptr))
+      return 1;
+  } else if (mc->sim_method == TFL_SIM_JACOBI) {                      // :275-303
+    if (!s->div.data) return fail(ctx, "simulate: state.div scratch is required for jacobi/pcg");
+    if (tfl_velocity_divergence_forward(ctx, &s->U, &s->flags, &s->div)) return 1;
+    const int iters = mc->max_iter > 0 ? mc->max_iter : 100;
+    if (tfl_solve_linear_system_jacobi(ctx, &s->p, &s->flags, &s->div, is3d, 0.0f, iters, nullptr, nullptr))
+      return 1;
+    if (tfl_velocity_update_forward(ctx, &s->U, &s->flags, &s->p)) return 1;
+  } else {
+    return fail(ctx, "mconf.simMethod (%d) is not a valid option", mc->sim_method);
+  }
+  if (set_const_vals(ctx, s)) return 1;                               // :321
+  return tfl_clamp(ctx, &s->U, -1e6f, 1e6f);                          // :326
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-buffer driver for the same step.
+// ---------------------------------------------------------------------------------------
+struct tfl_host_sim {
+  tfl_state st;
+  std::vector<void*> owned;
+  size_t cells = 0;
+  int nc = 3;
+};
+
+int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_t nx, int is_3d,
+                        const float* flags, const float* U_bc, const float* U_bc_inv, const float* d_bc,
+                        const float* d_bc_inv, tfl_host_sim** out) {
+  if (!out || !flags) return fail(ctx, "host_sim: bad arguments");
+  tfl_host_sim* hs = new tfl_host_sim();
+  memset(&hs->st, 0, sizeof(hs->st));
+  hs->nc = is_3d ? 3 : 2;
+  hs->cells = (size_t)nb * nz * ny * nx;
+  auto mk = [&](tfl_grid* g, int nc, const float* host) -> int {
+    g->nb = nb; g->nc = nc; g->nz = nz; g->ny = ny; g->nx = nx;
+    void* p = nullptr;
+    if (cudaMalloc(&p, hs->cells * nc * 4) != cudaSuccess) return 1;
+    hs->owned.push_back(p);
+    g->data = (float*)p;
+    if (host) cudaMemcpy(p, host, hs->cells * nc * 4, cudaMemcpyHostToDevice);
+    else cudaMemset(p, 0, hs->cells * nc * 4);
+    return 0;
+  };
+  int bad = 0;
+  bad |= mk(&hs->st.flags, 1, flags);
+  bad |= mk(&hs->st.p, 1, nullptr);
+  bad |= mk(&hs->st.U, hs->nc, nullptr);
+  bad |= mk(&hs->st.density, 1, nullptr);
+  bad |= mk(&hs->st.div, 1, nullptr);
+  if (U_bc && U_bc_inv) { bad |= mk(&hs->st.U_bc, hs->nc, U_bc); bad |= mk(&hs->st.U_bc_inv_mask, hs->nc, U_bc_inv); }
+  if (d_bc && d_bc_inv) { bad |= mk(&hs->st.density_bc, 1, d_bc); bad |= mk(&hs->st.density_bc_inv_mask, 1, d_bc_inv); }
+  if (bad) { tfl_host_sim_destroy(ctx, hs); return fail(ctx, "host_sim: cudaMalloc failed"); }
+  *out = hs;
+  return 0;
+}
+
+void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs) {
+  if (!hs) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (void* p : hs->owned) cudaFree(p);
+  delete hs;
+}
+
+int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
+                      const tfl_mconf* mc, tfl_cnn* cnn) {
+  if (!hs || !p || !U) return fail(ctx, "host_sim_step: nil buffer");
+  cudaStream_t st = ctx->stream;
+  tfl_state s = hs->st;
+  TFL_CUDA(ctx, cudaMemcpyAsync(s.p.data, p, hs->cells * 4, cudaMemcpyHostToDevice, st));
+  TFL_CUDA(ctx, cudaMemcpyAsync(s.U.data, U, hs->cells * 4 * hs->nc, cudaMemcpyHostToDevice, st));
+  if (density) TFL_CUDA(ctx, cudaMemcpyAsync(s.density.data, density, hs->cells * 4, cudaMemcpyHostToDevice, st));
+  else s.density.data = nullptr;
+  if (tfl_simulate_step(ctx, &s, mc, cnn)) return 1;
+  TFL_CUDA(ctx, cudaMemcpyAsync(p, s.p.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  TFL_CUDA(ctx, cudaMemcpyAsync(U, s.U.data, hs->cells * 4 * hs->nc, cudaMemcpyDeviceToHost, st));
+  if (density) TFL_CUDA(ctx, cudaMemcpyAsync(density, s.density.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  TFL_CUDA(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Host-callable launchers of the CUDA kernels (internal to libtfl; the public surface is
+// include/tfl.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/tfl.h"
+#include "tfl_device.cuh"
+
+namespace tfl {
+
+// ---- tfl_stencils.cu (-fmad=false) ----
+void launch_empty_domain(float* flags, const Geo& g, int bnd, cudaStream_t st);
+void launch_flags_to_occupancy(const float* flags, float* occ, long long n, unsigned long long* bad,
+                               cudaStream_t st);
+void launch_set_wall_bcs(float* U, const float* flags, const Geo& g, int as_mask, cudaStream_t st);
+void launch_divergence(const float* U, const float* flags, float* div, const Geo& g, cudaStream_t st);
+void launch_velocity_update(float* U, const float* flags, const float* p, const Geo& g, cudaStream_t st);
+void launch_add_buoyancy(float* U, const float* flags, const float* rho, const float s[3], const Geo& g,
+                         cudaStream_t st);
+void launch_add_gravity(float* U, const float* flags, const float f[3], const Geo& g, cudaStream_t st);
+int launch_vorticity(float* U, const float* flags, float strength, float* curl, float* cnorm, const Geo& g,
+                     cudaStream_t st);
+// g: range of the result; g_fwd: (wider, in slab mode) range of the forward pass.
+int launch_advect_scalar(float dt, const float* s, const float* U, const float* flags, int method,
+                         int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
+                         const Geo& g_fwd, cudaStream_t st);
+int launch_advect_vel(float dt, const float* U, const float* flags, int method, float strength, float* dst,
+                      float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st);
+void launch_jacobi_mask(const float* flags, unsigned char* mask, const Geo& g, cudaStream_t st);
+void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
+                        const Geo& g, cudaStream_t st);
+void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st);
+void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, cudaStream_t st);
+void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st);
+
+// CNN pre/post stages (exact float semantics of lib/model.lua's non-conv nodes).
+void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, const Geo& g,
+                           cudaStream_t st);
+void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_batch, float threshold,
+                      cudaStream_t st);
+void launch_cnn_inputs(const float* p_div, const float* U1, const float* flags, const float* scale,
+                       float* x0, const Geo& g, cudaStream_t st);
+void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, const float* scale,
+                       float* p_out, float* U_out, const Geo& g, cudaStream_t st);
+
+// ---- tfl_cnn.cu ----
+// Generic direct convolution (fp32 FMA): in [b][cin][z][y][x] -> out [b][cout][z][y][x].
+// wdev: device weights re-laid out as [cin][tap][cout_pad], bias [cout].
+int launch_conv_direct(const float* in, float* out, const float* wdev, const float* bdev, int cin, int cout,
+                       int ksize, int relu, const Geo& g, cudaStream_t st);
+
+}  // namespace tfl

@@ -1,0 +1,205 @@
+// Non-convolutional nodes of the projection graph (torch/lib/model.lua:27-401), compiled
+// with -fmad=false so they match the float arithmetic of the reference modules:
+//   tfluids.SetWallBcs      tfluids/set_wall_bcs.lua:29-48   (U * {0,1} mask)
+//   tfluids.VelocityDivergence, nn.StandardDeviation (lib/modules/variance.lua:44-76),
+//   nn.Clamp, nn.ApplyScale (lib/modules/apply_scale.lua), tfluids.FlagsToOccupancy,
+//   tfluids.VelocityUpdate  tfluids/velocity_update.lua:28-38
+#include "tfl_device.cuh"
+#include "tfl_kernels.h"
+
+namespace tfl {
+
+__device__ __forceinline__ bool thread_cell2(const Geo& g, int& b, int& k, int& j, int& i) {
+  i = blockIdx.x * blockDim.x + threadIdx.x;
+  j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
+  const int nzr = g.zhi - g.zlo;
+  b = zz / nzr;
+  k = g.zlo + (zz - b * nzr);
+  return i < g.nx && j < g.ny && b < g.nb;
+}
+static void launch_dims2(const Geo& g, dim3& grid, dim3& block) {
+  const int nzr = g.zhi - g.zlo;
+  block = (g.nz == 1) ? dim3(32, 8, 1) : dim3(32, 4, 2);
+  grid = dim3((g.nx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
+              ((long long)g.nb * nzr + block.z - 1) / block.z);
+}
+
+// Which velocity components setWallBcsForward zeroes at (i, j, k)
+// (third_party/tfluids.cc:926-1002); duplicated from tfl_stencils.cu on purpose so each
+// translation unit stays self-contained.
+__device__ __forceinline__ void wall_zero(const float* __restrict__ fl, const Geo& g, int k, int j, int i,
+                                          bool z[3]) {
+  z[0] = z[1] = z[2] = false;
+  const int fc = flag_i(fl, g, k, j, i);
+  const bool cf = fc & kFluid, co = fc & kObstacle;
+  if (!cf && !co) return;
+  const int kg = k + g.zoff;
+  if (i > 0) {
+    const int f = flag_i(fl, g, k, j, i - 1);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[0] = true;
+  }
+  if (j > 0) {
+    const int f = flag_i(fl, g, k, j - 1, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[1] = true;
+  }
+  if (kg > 0) {
+    const int f = flag_i(fl, g, local_z(g, kg - 1), j, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[2] = true;
+  }
+  if (cf) {
+    if ((i > 0 && (flag_i(fl, g, k, j, i - 1) & kStick)) ||
+        (i < g.nx - 1 && (flag_i(fl, g, k, j, i + 1) & kStick))) { z[1] = true; if (g.is3d) z[2] = true; }
+    if ((j > 0 && (flag_i(fl, g, k, j - 1, i) & kStick)) ||
+        (j < g.ny - 1 && (flag_i(fl, g, k, j + 1, i) & kStick))) { z[0] = true; if (g.is3d) z[2] = true; }
+    if (g.is3d && ((kg > 0 && (flag_i(fl, g, local_z(g, kg - 1), j, i) & kStick)) ||
+                   (kg < g.gnz - 1 && (flag_i(fl, g, local_z(g, kg + 1), j, i) & kStick)))) {
+      z[0] = true; z[1] = true;
+    }
+  }
+}
+
+// U1 = U * wallmask; sums[b] += (sum U1, sum U1^2) over the launch range (double).
+__global__ void k_cnn_mask_stats(const float* __restrict__ U, const float* __restrict__ flags,
+                                 float* __restrict__ U1, double* __restrict__ sums, Geo g) {
+  int b, k, j, i;
+  const bool live = thread_cell2(g, b, k, j, i);
+  double s = 0.0, ss = 0.0;
+  if (live) {
+    bool z[3];
+    wall_zero(flags + b * g.n, g, k, j, i, z);
+    const long long c = (long long)b * g.nc * g.n + cell(g, k, j, i);
+    for (int a = 0; a < g.nc; a++) {
+      float u = U[c + a * g.n];
+      if (z[a]) u = u * 0.0f;
+      U1[c + a * g.n] = u;
+      const float sq = u * u;
+      s += (double)u;
+      ss += (double)sq;
+    }
+  }
+  // A block may straddle two batch entries only when nb > 1 and the z range is odd; keep
+  // it simple and correct: reduce per warp, then one atomic per warp and batch entry.
+  const unsigned lane = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  const int b0 = __shfl_sync(0xffffffffu, live ? b : -1, 0);
+  const bool uniform = __all_sync(0xffffffffu, (live ? b : -1) == b0 || !live);
+  if (uniform) {
+    int bb = live ? b : -1;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(0xffffffffu, s, o);
+      ss += __shfl_down_sync(0xffffffffu, ss, o);
+      bb = max(bb, __shfl_down_sync(0xffffffffu, bb, o));
+    }
+    if ((lane & 31) == 0 && bb >= 0) {
+      atomicAdd(sums + 2 * bb, s);
+      atomicAdd(sums + 2 * bb + 1, ss);
+    }
+  } else if (live) {
+    atomicAdd(sums + 2 * b, s);
+    atomicAdd(sums + 2 * b + 1, ss);
+  }
+}
+
+// nn.StandardDeviation + nn.Clamp(threshold, inf): float tensor ops on the two sums.
+__global__ void k_cnn_scale(const double* __restrict__ sums, float* __restrict__ scale, int nb,
+                            long long n, float threshold) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const float sum = (float)sums[2 * b], sumsq = (float)sums[2 * b + 1];
+  float out = sumsq * (float)n;
+  out = out + (-1.0f) * (sum * sum);
+  out = out / (float)((double)n * (double)(n - 1));
+  out = sqrtf(out);
+  scale[b] = (out < threshold) ? threshold : out;      // also maps NaN -> NaN like nn.Clamp? (NaN < t is false)
+}
+
+// x0 = [pDiv / scale, div(U1) / scale, occupancy(flags)]
+__global__ void k_cnn_inputs(const float* __restrict__ p_div, const float* __restrict__ U1,
+                             const float* __restrict__ flags, const float* __restrict__ scale,
+                             float* __restrict__ x0, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell2(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float sc = __ldg(scale + b);
+  const float* ub = U1 + (long long)b * g.nc * g.n;
+  const int f = flag_i(flags + b * g.n, g, k, j, i);
+  float dv = 0.0f;
+  if (!on_border(g, k, j, i) && (f & kFluid)) {
+    dv = __ldg(ub + c) - __ldg(ub + c + 1) + __ldg(ub + g.n + c) - __ldg(ub + g.n + c + g.nx);
+    if (g.is3d) dv += (__ldg(ub + 2 * g.n + c) - __ldg(ub + 2 * g.n + c + (long long)g.nx * g.ny));
+  }
+  float* xb = x0 + (long long)b * 3 * g.n + c;
+  xb[0] = __ldg(p_div + b * g.n + c) / sc;
+  xb[g.n] = dv / sc;
+  xb[2 * g.n] = (f == kFluid) ? 0.0f : ((f == kObstacle) ? 1.0f : -1.0f);
+}
+
+// U = setWallBcs(velocityUpdate(U1 / scale, p_net) * scale);  p = p_net * scale.
+__global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __restrict__ U1,
+                             const float* __restrict__ flags, const float* __restrict__ scale,
+                             float* __restrict__ p_out, float* __restrict__ U_out, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell2(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float sc = __ldg(scale + b);
+  const float* fl = flags + b * g.n;
+  const float* pb = p_net + b * g.n;
+  const float* ub = U1 + (long long)b * g.nc * g.n;
+  const float pc = __ldg(pb + c);
+  float u[3];
+  for (int a = 0; a < g.nc; a++) u[a] = __ldg(ub + a * g.n + c) / sc;
+  if (!on_border(g, k, j, i)) {
+    const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+    const int fc = flag_i(fl, g, k, j, i);
+    int fn[3];
+    fn[0] = flag_i(fl, g, k, j, i - 1);
+    fn[1] = flag_i(fl, g, k, j - 1, i);
+    fn[2] = g.is3d ? flag_i(fl, g, k - 1, j, i) : 0;
+    if (fc & kFluid) {
+      for (int a = 0; a < g.nc; a++) {
+        if (fn[a] & kFluid) u[a] -= (pc - __ldg(pb + c - st[a]));
+        if (fn[a] & kEmpty) u[a] -= pc;
+      }
+    } else if ((fc & kEmpty) && !(fc & kOutflow)) {
+      for (int a = 0; a < g.nc; a++) {
+        if (fn[a] & kFluid) u[a] += __ldg(pb + c - st[a]);
+        else u[a] = 0.0f;
+      }
+    }
+  }
+  bool z[3];
+  wall_zero(fl, g, k, j, i, z);
+  float* uo = U_out + (long long)b * g.nc * g.n + c;
+  for (int a = 0; a < g.nc; a++) {
+    float v = u[a] * sc;
+    if (z[a]) v = v * 0.0f;
+    uo[a * g.n] = v;
+  }
+  p_out[b * g.n + c] = pc * sc;
+}
+
+#define TFL_LAUNCH3B(kernel, g, st, ...)           \
+  do {                                             \
+    dim3 grid_, block_;                            \
+    launch_dims2(g, grid_, block_);                \
+    kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
+  } while (0)
+
+void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, const Geo& g,
+                           cudaStream_t st) {
+  TFL_LAUNCH3B(k_cnn_mask_stats, g, st, U, flags, U1, sums, g);
+}
+void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_batch, float threshold,
+                      cudaStream_t st) {
+  k_cnn_scale<<<(nb + 31) / 32, 32, 0, st>>>(sums, scale, nb, n_per_batch, threshold);
+}
+void launch_cnn_inputs(const float* p_div, const float* U1, const float* flags, const float* scale,
+                       float* x0, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3B(k_cnn_inputs, g, st, p_div, U1, flags, scale, x0, g);
+}
+void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, const float* scale,
+                       float* p_out, float* U_out, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3B(k_cnn_finish, g, st, p_net, U1, flags, scale, p_out, U_out, g);
+}
+
+}  // namespace tfl

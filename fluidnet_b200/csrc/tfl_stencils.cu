@@ -1,0 +1,800 @@
+// MAC-grid stencil kernels of the Eulerian step (everything except the conv stack).
+// Compiled with -fmad=false: results are bit-identical to the reference CPU operators
+// (see oracle/ and tests/).  One thread per cell, x fastest (coalesced rows); neighbour
+// reuse comes from L1/L2.  Launchers at the bottom are called by tfl_api.cu.
+//
+// Reference operators restated here (paths relative to /root/reference/torch/tfluids):
+//   advectScalar   third_party/tfluids.cc:23-588     advectVel   third_party/tfluids.cc:594-920
+//   setWallBcs     third_party/tfluids.cc:926-1002   divergence  third_party/tfluids.cc:1008-1066
+//   velocityUpdate third_party/tfluids.cc:1072-1156  buoyancy    third_party/tfluids.cc:1162-1233
+//   addGravity     third_party/tfluids.cc:1239-1306  vorticity   third_party/tfluids.cc:1312-1458
+//   Jacobi         generic/tfluids.cu:1765-1927      emptyDomain generic/tfluids.cc:136-172
+//   flagsToOccupancy generic/tfluids.cu:355-401
+#include "tfl_device.cuh"
+#include "tfl_kernels.h"
+
+namespace tfl {
+
+// (b, k, j, i) of this thread; returns false if outside the launch range.
+__device__ __forceinline__ bool thread_cell(const Geo& g, int& b, int& k, int& j, int& i) {
+  i = blockIdx.x * blockDim.x + threadIdx.x;
+  j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
+  const int nzr = g.zhi - g.zlo;
+  b = zz / nzr;
+  k = g.zlo + (zz - b * nzr);
+  return i < g.nx && j < g.ny && b < g.nb;
+}
+
+static void launch_dims(const Geo& g, dim3& grid, dim3& block) {
+  const int nzr = g.zhi - g.zlo;
+  if (g.nz == 1) block = dim3(32, 8, 1);
+  else block = dim3(32, 4, 2);
+  if (g.nx > 32 && g.nx % 64 == 0) { block.x = 64; block.y = (g.nz == 1) ? 4 : 2; }
+  grid = dim3((g.nx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
+              ((long long)g.nb * nzr + block.z - 1) / block.z);
+}
+
+// ---------------------------------------------------------------------------------------
+// emptyDomain / flagsToOccupancy
+// ---------------------------------------------------------------------------------------
+__global__ void k_empty_domain(float* __restrict__ flags, Geo g, int bnd) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const int kg = k + g.zoff;
+  const bool border = i < bnd || i > g.nx - 1 - bnd || j < bnd || j > g.ny - 1 - bnd ||
+                      (g.is3d && (kg < bnd || kg > g.gnz - 1 - bnd));
+  flags[b * g.n + cell(g, k, j, i)] = border ? (float)kObstacle : (float)kFluid;
+}
+
+__global__ void k_flags_to_occupancy(const float* __restrict__ flags, float* __restrict__ occ,
+                                     long long n, unsigned long long* bad) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int f = (int)flags[t];
+  float o;
+  if (f == kFluid) o = 0.0f;
+  else if (f == kObstacle) o = 1.0f;
+  else { o = -1.0f; atomicAdd(bad, 1ULL); }     // CUDA reference writes -1 (generic/tfluids.cu:362-370)
+  occ[t] = o;
+}
+
+// ---------------------------------------------------------------------------------------
+// setWallBcsForward
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void wall_bc_zero_mask(const float* __restrict__ fl, const Geo& g, int k,
+                                                  int j, int i, bool z[3]) {
+  z[0] = z[1] = z[2] = false;
+  const int fc = flag_i(fl, g, k, j, i);
+  const bool cf = fc & kFluid, co = fc & kObstacle;
+  if (!cf && !co) return;
+  const int kg = k + g.zoff;
+  if (i > 0) {
+    const int f = flag_i(fl, g, k, j, i - 1);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[0] = true;
+  }
+  if (j > 0) {
+    const int f = flag_i(fl, g, k, j - 1, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[1] = true;
+  }
+  if (kg > 0) {
+    const int f = flag_i(fl, g, local_z(g, kg - 1), j, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[2] = true;
+  }
+  if (cf) {
+    if ((i > 0 && (flag_i(fl, g, k, j, i - 1) & kStick)) ||
+        (i < g.nx - 1 && (flag_i(fl, g, k, j, i + 1) & kStick))) { z[1] = true; if (g.is3d) z[2] = true; }
+    if ((j > 0 && (flag_i(fl, g, k, j - 1, i) & kStick)) ||
+        (j < g.ny - 1 && (flag_i(fl, g, k, j + 1, i) & kStick))) { z[0] = true; if (g.is3d) z[2] = true; }
+    if (g.is3d && ((kg > 0 && (flag_i(fl, g, local_z(g, kg - 1), j, i) & kStick)) ||
+                   (kg < g.gnz - 1 && (flag_i(fl, g, local_z(g, kg + 1), j, i) & kStick)))) {
+      z[0] = true; z[1] = true;
+    }
+  }
+}
+
+__global__ void k_set_wall_bcs(float* __restrict__ U, const float* __restrict__ flags, Geo g,
+                               int as_mask) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  bool z[3];
+  wall_bc_zero_mask(flags + b * g.n, g, k, j, i, z);
+  float* ub = U + (long long)b * g.nc * g.n + cell(g, k, j, i);
+  for (int c = 0; c < g.nc; c++)
+    if (z[c]) ub[c * g.n] = as_mask ? ub[c * g.n] * 0.0f : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------
+// velocityDivergenceForward  (returns u(i)-u(i+1)+..., i.e. minus the divergence)
+// ---------------------------------------------------------------------------------------
+__global__ void k_divergence(const float* __restrict__ U, const float* __restrict__ flags,
+                             float* __restrict__ div, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float* ub = U + (long long)b * g.nc * g.n;
+  float r = 0.0f;
+  if (!on_border(g, k, j, i) && (flag_i(flags + b * g.n, g, k, j, i) & kFluid)) {
+    r = __ldg(ub + c) - __ldg(ub + c + 1) + __ldg(ub + g.n + c) - __ldg(ub + g.n + c + g.nx);
+    if (g.is3d) r += (__ldg(ub + 2 * g.n + c) - __ldg(ub + 2 * g.n + c + (long long)g.nx * g.ny));
+  }
+  div[b * g.n + c] = r;
+}
+
+// ---------------------------------------------------------------------------------------
+// velocityUpdateForward
+// ---------------------------------------------------------------------------------------
+__global__ void k_velocity_update(float* __restrict__ U, const float* __restrict__ flags,
+                                  const float* __restrict__ p, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  if (on_border(g, k, j, i)) return;
+  const float* fl = flags + b * g.n;
+  const float* pb = p + b * g.n;
+  float* ub = U + (long long)b * g.nc * g.n;
+  const long long c = cell(g, k, j, i);
+  const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+  const int fc = flag_i(fl, g, k, j, i);
+  int fn[3];
+  fn[0] = flag_i(fl, g, k, j, i - 1);
+  fn[1] = flag_i(fl, g, k, j - 1, i);
+  fn[2] = g.is3d ? flag_i(fl, g, k - 1, j, i) : 0;
+  const float pc = __ldg(pb + c);
+  if (fc & kFluid) {
+    for (int a = 0; a < g.nc; a++) {
+      float u = ub[a * g.n + c];
+      if (fn[a] & kFluid) u -= (pc - __ldg(pb + c - st[a]));
+      if (fn[a] & kEmpty) u -= pc;
+      ub[a * g.n + c] = u;
+    }
+  } else if ((fc & kEmpty) && !(fc & kOutflow)) {
+    for (int a = 0; a < g.nc; a++) {
+      float u = ub[a * g.n + c];
+      if (fn[a] & kFluid) u += __ldg(pb + c - st[a]);
+      else u = 0.0f;
+      ub[a * g.n + c] = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// addBuoyancy / addGravity
+// ---------------------------------------------------------------------------------------
+__global__ void k_add_buoyancy(float* __restrict__ U, const float* __restrict__ flags,
+                               const float* __restrict__ rho, float sx, float sy_, float sz_, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  if (on_border(g, k, j, i)) return;
+  const float* fl = flags + b * g.n;
+  if (!(flag_i(fl, g, k, j, i) & kFluid)) return;
+  const float* rb = rho + b * g.n;
+  float* ub = U + (long long)b * g.nc * g.n;
+  const long long c = cell(g, k, j, i);
+  const float rc = __ldg(rb + c);
+  if (flag_i(fl, g, k, j, i - 1) & kFluid) ub[c] += (0.5f * sx * (rc + __ldg(rb + c - 1)));
+  if (flag_i(fl, g, k, j - 1, i) & kFluid) ub[g.n + c] += (0.5f * sy_ * (rc + __ldg(rb + c - g.nx)));
+  if (g.is3d && (flag_i(fl, g, k - 1, j, i) & kFluid))
+    ub[2 * g.n + c] += (0.5f * sz_ * (rc + __ldg(rb + c - (long long)g.nx * g.ny)));
+}
+
+__global__ void k_add_gravity(float* __restrict__ U, const float* __restrict__ flags, float fx,
+                              float fy, float fz, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  if (on_border(g, k, j, i)) return;
+  const float* fl = flags + b * g.n;
+  const int fc = flag_i(fl, g, k, j, i);
+  const bool cf = fc & kFluid, ce = fc & kEmpty;
+  if (!cf && !ce) return;
+  float* ub = U + (long long)b * g.nc * g.n;
+  const long long c = cell(g, k, j, i);
+  int f = flag_i(fl, g, k, j, i - 1);
+  if ((f & kFluid) || (cf && (f & kEmpty))) ub[c] += fx;
+  f = flag_i(fl, g, k, j - 1, i);
+  if ((f & kFluid) || (cf && (f & kEmpty))) ub[g.n + c] += fy;
+  if (g.is3d) {
+    f = flag_i(fl, g, k - 1, j, i);
+    if ((f & kFluid) || (cf && (f & kEmpty))) ub[2 * g.n + c] += fz;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// vorticityConfinement: two kernels instead of the reference's four passes.
+//   (1) curl + |curl| straight from the face velocities (centred velocities are
+//       recomputed per neighbour, bit-identical to storing them);
+//   (2) confinement force recomputed at the 4 cells each face needs, then applied.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 centered_or_zero(const float* __restrict__ Ub, const Geo& g, int k,
+                                               int j, int i) {
+  if (on_border(g, k, j, i)) return V3{0.0f, 0.0f, 0.0f};
+  return mac_centered(Ub, g, k, j, i);
+}
+
+__global__ void k_vort_curl(const float* __restrict__ U, float* __restrict__ curl,
+                            float* __restrict__ cnorm, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const float* ub = U + (long long)b * g.nc * g.n;
+  const long long c = cell(g, k, j, i);
+  V3 w = {0.0f, 0.0f, 0.0f};
+  float nrm = 0.0f;
+  if (!on_border(g, k, j, i)) {
+    const V3 xm = centered_or_zero(ub, g, k, j, i - 1), xp = centered_or_zero(ub, g, k, j, i + 1);
+    const V3 ym = centered_or_zero(ub, g, k, j - 1, i), yp = centered_or_zero(ub, g, k, j + 1, i);
+    w.z = 0.5f * ((xp.y - xm.y) - (yp.x - ym.x));
+    if (g.is3d) {
+      const V3 zm = centered_or_zero(ub, g, k - 1, j, i), zp = centered_or_zero(ub, g, k + 1, j, i);
+      w.x = 0.5f * ((yp.z - ym.z) - (zp.y - zm.y));
+      w.y = 0.5f * ((zp.x - zm.x) - (xp.z - xm.z));
+    }
+    nrm = norm3(w);
+  }
+  float* cb = curl + (long long)b * 3 * g.n;
+  cb[c] = w.x; cb[g.n + c] = w.y; cb[2 * g.n + c] = w.z;
+  cnorm[b * g.n + c] = nrm;
+}
+
+__device__ __forceinline__ V3 conf_force(const float* __restrict__ cb, const float* __restrict__ cn,
+                                         const Geo& g, int k, int j, int i, float strength) {
+  if (on_border(g, k, j, i)) return V3{0.0f, 0.0f, 0.0f};
+  const long long c = cell(g, k, j, i);
+  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  V3 gr = {0.0f, 0.0f, 0.0f};
+  gr.x = 0.5f * (__ldg(cn + c + 1) - __ldg(cn + c - 1));
+  gr.y = 0.5f * (__ldg(cn + c + sy) - __ldg(cn + c - sy));
+  if (g.is3d) gr.z = 0.5f * (__ldg(cn + c + sz) - __ldg(cn + c - sz));
+  const float gn = norm3(gr);
+  if (gn > 1e-6f) { gr.x /= gn; gr.y /= gn; gr.z /= gn; } else { gr.x = gr.y = gr.z = 0.0f; }
+  const V3 w = {__ldg(cb + c), __ldg(cb + g.n + c), __ldg(cb + 2 * g.n + c)};
+  V3 f;
+  f.x = ((gr.y * w.z) - (gr.z * w.y)) * strength;
+  f.y = ((gr.z * w.x) - (gr.x * w.z)) * strength;
+  f.z = ((gr.x * w.y) - (gr.y * w.x)) * strength;
+  return f;
+}
+
+__global__ void k_vort_apply(float* __restrict__ U, const float* __restrict__ flags,
+                             const float* __restrict__ curl, const float* __restrict__ cnorm,
+                             float strength, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  if (on_border(g, k, j, i)) return;
+  const float* fl = flags + b * g.n;
+  const int fc = flag_i(fl, g, k, j, i);
+  const bool cf = fc & kFluid, ce = fc & kEmpty;
+  if (!cf && !ce) return;
+  const float* cb = curl + (long long)b * 3 * g.n;
+  const float* cn = cnorm + b * g.n;
+  float* ub = U + (long long)b * g.nc * g.n;
+  const long long c = cell(g, k, j, i);
+  const V3 f0 = conf_force(cb, cn, g, k, j, i, strength);
+  int f = flag_i(fl, g, k, j, i - 1);
+  if ((f & kFluid) || (cf && (f & kEmpty)))
+    ub[c] += (0.5f * (conf_force(cb, cn, g, k, j, i - 1, strength).x + f0.x));
+  f = flag_i(fl, g, k, j - 1, i);
+  if ((f & kFluid) || (cf && (f & kEmpty)))
+    ub[g.n + c] += (0.5f * (conf_force(cb, cn, g, k, j - 1, i, strength).y + f0.y));
+  if (g.is3d) {
+    f = flag_i(fl, g, k - 1, j, i);
+    if ((f & kFluid) || (cf && (f & kEmpty)))
+      ub[2 * g.n + c] += (0.5f * (conf_force(cb, cn, g, k - 1, j, i, strength).z + f0.z));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// advectScalar
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float sample_scalar(const float* __restrict__ src, const float* __restrict__ fl,
+                                               const Geo& g, V3 pos, bool outside) {
+  return outside ? lerp_block(src, g, pos) : lerp_block_fluid(src, fl, g, pos);
+}
+__device__ __forceinline__ V3 sample_vel(const float* __restrict__ ub, const Geo& g, V3 pos) {
+  const Lerp q = build_index(g, pos);
+  const long long o = corner(g, q);
+  V3 r;
+  r.x = lerp_at(ub, g, q, o);
+  r.y = lerp_at(ub + g.n, g, q, o);
+  r.z = g.is3d ? lerp_at(ub + 2 * g.n, g, q, o) : 0.0f;
+  return r;
+}
+
+// One semi-Lagrangian pass for an interior cell.  `pos_out` receives the trace end
+// point ("SavePos" variants) when non-null.
+template <int METHOD>
+__device__ __forceinline__ float advect_scalar_cell(const float* __restrict__ fl, const float* __restrict__ ub,
+                                                    const float* __restrict__ src, const Geo& g, float dt,
+                                                    int k, int j, int i, bool outside, V3* pos_out) {
+  const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
+  if (METHOD == TFL_ADVECT_EULER || METHOD == TFL_ADVECT_MACCORMACK) {
+    const V3 c = mac_centered(ub, g, k, j, i);
+    const V3 p = {start.x - c.x * dt, start.y - c.y * dt, start.z - c.z * dt};
+    return lerp_block(src, g, p);
+  }
+  if (!(flag_i(fl, g, k, j, i) & kFluid)) {
+    if (pos_out) *pos_out = start;
+    return __ldg(src + cell(g, k, j, i));
+  }
+  const V3 c = mac_centered(ub, g, k, j, i);
+  if (METHOD == TFL_ADVECT_EULER_OURS || METHOD == TFL_ADVECT_MACCORMACK_OURS) {
+    V3 back;
+    line_trace(fl, g, start, scale3(c, -dt), &back);
+    if (pos_out) *pos_out = back;
+    return sample_scalar(src, fl, g, back, outside);
+  }
+  if (METHOD == TFL_ADVECT_RK2_OURS) {
+    V3 half, back;
+    if (line_trace(fl, g, start, scale3(c, -dt * 0.5f), &half)) return sample_scalar(src, fl, g, half, outside);
+    const V3 v = sample_vel(ub, g, half);
+    line_trace(fl, g, start, scale3(v, -dt), &back);
+    return sample_scalar(src, fl, g, back, outside);
+  }
+  // RK3 (CPU behaviour: a third-stage hit samples at the third-stage position,
+  // third_party/tfluids.cc:117-126).
+  V3 p2, p3, back;
+  if (line_trace(fl, g, start, scale3(c, -dt * 0.5f), &p2)) return sample_scalar(src, fl, g, p2, outside);
+  const V3 k2 = sample_vel(ub, g, p2);
+  if (line_trace(fl, g, start, scale3(k2, -dt * 0.75f), &p3)) return sample_scalar(src, fl, g, p3, outside);
+  const V3 k3 = sample_vel(ub, g, p3);
+  const float w1 = -dt * (float)(2.0 / 9.0), w2 = -dt * (float)(3.0 / 9.0), w3 = -dt * (float)(4.0 / 9.0);
+  const V3 a1 = scale3(c, w1), a2 = scale3(k2, w2), a3 = scale3(k3, w3);
+  const V3 disp = {(a1.x + a2.x) + a3.x, (a1.y + a2.y) + a3.y, (a1.z + a2.z) + a3.z};
+  line_trace(fl, g, start, disp, &back);
+  return sample_scalar(src, fl, g, back, outside);
+}
+
+template <int METHOD>
+__global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* __restrict__ U,
+                                      const float* __restrict__ flags, float* __restrict__ out,
+                                      float* __restrict__ pos_out, float dt, int outside, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  float v = 0.0f;
+  V3 pos = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
+  if (!on_border(g, k, j, i)) {
+    v = advect_scalar_cell<METHOD>(flags + b * g.n, U + (long long)b * g.nc * g.n, s + b * g.n, g, dt, k,
+                                   j, i, outside != 0, pos_out ? &pos : nullptr);
+  }
+  out[b * g.n + c] = v;
+  if (pos_out) {
+    float* pp = pos_out + (long long)b * g.nc * g.n + c;
+    pp[0] = pos.x; pp[g.n] = pos.y;
+    if (g.is3d) pp[2 * g.n] = pos.z;
+  }
+}
+
+// MacCormack (ours): backward trace on the forward field + correction + clamp to the
+// fluid neighbourhood of the forward trace position, fused
+// (third_party/tfluids.cc:521-583, 222-234, 331-413).
+__global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const float* __restrict__ fwd,
+                                           const float* __restrict__ fwd_pos, const float* __restrict__ U,
+                                           const float* __restrict__ flags, float* __restrict__ dst,
+                                           float dt, float strength, int outside, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float* fl = flags + b * g.n;
+  const float* sb = s + b * g.n;
+  const float* fb = fwd + b * g.n;
+  const float fw = __ldg(fb + c);
+  const bool border = on_border(g, k, j, i);
+  float bw = 0.0f;
+  if (!border)
+    bw = advect_scalar_cell<TFL_ADVECT_MACCORMACK_OURS>(fl, U + (long long)b * g.nc * g.n, fb, g, -dt, k,
+                                                        j, i, outside != 0, nullptr);
+  float v = fw;
+  if (flag_i(fl, g, k, j, i) & kFluid) {
+    const float diff = __ldg(sb + c) - bw;
+    v = (float)((double)v + ((double)strength * 0.5) * (double)diff);
+  }
+  if (!border) {
+    const float* pp = fwd_pos + (long long)b * g.nc * g.n + c;
+    const float px = __ldg(pp), py = __ldg(pp + g.n), pz = g.is3d ? __ldg(pp + 2 * g.n) : 0.0f;
+    const int i0 = clamp_i((int)px, 0, g.nx - 1), j0 = clamp_i((int)py, 0, g.ny - 1);
+    const int k0 = g.is3d ? clamp_i((int)pz, 0, g.gnz - 1) : 0;
+    float lo = INFINITY, hi = -INFINITY;
+    int found = 0;
+    for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
+      if (kk < 0 || kk >= g.gnz) continue;
+      const int kl = local_z(g, kk);
+      for (int jj = j0 - 1; jj <= j0 + 1; jj++) {
+        if (jj < 0 || jj >= g.ny) continue;
+        for (int ii = i0 - 1; ii <= i0 + 1; ii++) {
+          if (ii < 0 || ii >= g.nx) continue;
+          if (outside || (flag_i(fl, g, kl, jj, ii) & kFluid)) {
+            const float t = __ldg(sb + cell(g, kl, jj, ii));
+            if (t < lo) lo = t;
+            if (t > hi) hi = t;
+            found++;
+          }
+        }
+      }
+    }
+    v = (found < 1) ? fw : clamp_f(v, lo, hi);
+  }
+  dst[b * g.n + c] = v;
+}
+
+// MacCormack (Manta): third_party/tfluids.cc:249-325.
+__global__ void k_advect_scalar_pass2_manta(const float* __restrict__ s, const float* __restrict__ fwd,
+                                            const float* __restrict__ U, const float* __restrict__ flags,
+                                            float* __restrict__ dst, float dt, float strength, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float* fl = flags + b * g.n;
+  const float* sb = s + b * g.n;
+  const float* fb = fwd + b * g.n;
+  const float* ub = U + (long long)b * g.nc * g.n;
+  const float fw = __ldg(fb + c);
+  const bool border = on_border(g, k, j, i);
+  float bw = 0.0f;
+  if (!border) bw = advect_scalar_cell<TFL_ADVECT_MACCORMACK>(fl, ub, fb, g, -dt, k, j, i, true, nullptr);
+  float v = fw;
+  if (flag_i(fl, g, k, j, i) & kFluid) {
+    const float diff = __ldg(sb + c) - bw;
+    v = (float)((double)v + ((double)strength * 0.5) * (double)diff);
+  }
+  if (!border) {
+    const V3 vel = scale3(mac_centered(ub, g, k, j, i), dt);
+    const float fi = (float)i, fj = (float)j, fk = (float)(k + g.zoff);
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    bool bail = false;
+    for (int l = 0; l < 2 && !bail; l++) {
+      const int px = l == 0 ? (int)(fi - vel.x) : (int)(fi + vel.x);
+      const int py = l == 0 ? (int)(fj - vel.y) : (int)(fj + vel.y);
+      const int pz = l == 0 ? (int)(fk - vel.z) : (int)(fk + vel.z);
+      const int i0 = clamp_i(px, 0, g.nx - 2), j0 = clamp_i(py, 0, g.ny - 2);
+      const int k0 = clamp_i(pz, 0, g.is3d ? g.gnz - 2 : 1);
+      const int i1 = i0 + 1, j1 = j0 + 1, k1 = g.is3d ? k0 + 1 : k0;
+      bool inb = i0 >= 0 && j0 >= 0 && i1 < g.nx && j1 < g.ny;
+      if (g.is3d) inb = inb && k0 >= 0 && k1 < g.gnz; else inb = inb && k0 == 0 && k1 == 0;
+      if (!inb) { bail = true; break; }
+      const int kl0 = local_z(g, k0), kl1 = g.is3d ? local_z(g, k1) : kl0;
+#define TFL_MM(kk, jj, ii) { const float t = __ldg(sb + cell(g, kk, jj, ii)); if (t < lo) lo = t; if (t > hi) hi = t; }
+      TFL_MM(kl0, j0, i0) TFL_MM(kl0, j0, i1) TFL_MM(kl0, j1, i0) TFL_MM(kl0, j1, i1)
+      if (g.is3d) { TFL_MM(kl1, j0, i0) TFL_MM(kl1, j0, i1) TFL_MM(kl1, j1, i0) TFL_MM(kl1, j1, i1) }
+#undef TFL_MM
+    }
+    v = bail ? fw : clamp_f(v, lo, hi);
+    const int fx = (int)((fi + 0.5f) - vel.x), fy = (int)((fj + 0.5f) - vel.y), fz = (int)((fk + 0.5f) - vel.z);
+    const int bx = (int)((fi + 0.5f) + vel.x), by = (int)((fj + 0.5f) + vel.y), bz = (int)((fk + 0.5f) + vel.z);
+    const int ux = g.nx - 1, uy = g.ny - 1, uz = g.gnz - 1;
+    if (fx < 0 || fy < 0 || fz < 0 || bx < 0 || by < 0 || bz < 0 || fx > ux || fy > uy ||
+        (fz > uz && g.is3d) || bx > ux || by > uy || (bz > uz && g.is3d) ||
+        (flag_i(fl, g, local_z(g, fz), fy, fx) & kObstacle) ||
+        (flag_i(fl, g, local_z(g, bz), by, bx) & kObstacle)) {
+      v = fw;
+    }
+  }
+  dst[b * g.n + c] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// advectVel
+// ---------------------------------------------------------------------------------------
+template <bool OURS>
+__device__ __forceinline__ V3 advect_mac_cell(const float* __restrict__ fl, const float* __restrict__ ub,
+                                              const float* __restrict__ src, const Geo& g, float dt, int k,
+                                              int j, int i) {
+  V3 r;
+  if (OURS && !(flag_i(fl, g, k, j, i) & kFluid)) {
+    const long long c = cell(g, k, j, i);
+    r.x = __ldg(src + c); r.y = __ldg(src + g.n + c); r.z = g.is3d ? __ldg(src + 2 * g.n + c) : 0.0f;
+    return r;
+  }
+  const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
+  V3 p;
+  if (OURS) {
+    line_trace(fl, g, start, scale3(mac_at_x(ub, g, k, j, i), -dt), &p);
+    r.x = lerp_block(src, g, p);
+    line_trace(fl, g, start, scale3(mac_at_y(ub, g, k, j, i), -dt), &p);
+    r.y = lerp_block(src + g.n, g, p);
+    if (g.is3d) {
+      line_trace(fl, g, start, scale3(mac_at_z(ub, g, k, j, i), -dt), &p);
+      r.z = lerp_block(src + 2 * g.n, g, p);
+    } else {
+      r.z = 0.0f;
+    }
+  } else {
+    V3 v = scale3(mac_at_x(ub, g, k, j, i), dt);
+    p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
+    r.x = lerp_block(src, g, p);
+    v = scale3(mac_at_y(ub, g, k, j, i), dt);
+    p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
+    r.y = lerp_block(src + g.n, g, p);
+    if (g.is3d) {
+      v = scale3(mac_at_z(ub, g, k, j, i), dt);
+      p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
+      r.z = lerp_block(src + 2 * g.n, g, p);
+    } else {
+      r.z = 0.0f;
+    }
+  }
+  return r;
+}
+
+template <bool OURS>
+__global__ void k_advect_vel_pass1(const float* __restrict__ U, const float* __restrict__ flags,
+                                   float* __restrict__ out, float dt, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float* ub = U + (long long)b * g.nc * g.n;
+  V3 v = {0.0f, 0.0f, 0.0f};
+  if (!on_border(g, k, j, i)) v = advect_mac_cell<OURS>(flags + b * g.n, ub, ub, g, dt, k, j, i);
+  float* ob = out + (long long)b * g.nc * g.n + c;
+  ob[0] = v.x; ob[g.n] = v.y;
+  if (g.is3d) ob[2 * g.n] = v.z;
+}
+
+__device__ __forceinline__ float clamp_component_mac(const float* __restrict__ orig_c, const Geo& g,
+                                                     float val, float fwd, int kglob, int j, int i, V3 vel) {
+  const float fi = (float)i, fj = (float)j, fk = (float)kglob;
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (int l = 0; l < 2; l++) {
+    const int px = l == 0 ? (int)(fi - vel.x) : (int)(fi + vel.x);
+    const int py = l == 0 ? (int)(fj - vel.y) : (int)(fj + vel.y);
+    const int pz = l == 0 ? (int)(fk - vel.z) : (int)(fk + vel.z);
+    const int i0 = clamp_i(px, 0, g.nx - 2), j0 = clamp_i(py, 0, g.ny - 2);
+    const int k0 = clamp_i(pz, 0, g.is3d ? g.gnz - 2 : 1);
+    const int i1 = i0 + 1, j1 = j0 + 1, k1 = g.is3d ? k0 + 1 : k0;
+    bool inb = i0 >= 0 && j0 >= 0 && i1 < g.nx && j1 < g.ny;
+    if (g.is3d) inb = inb && k0 >= 0 && k1 < g.gnz; else inb = inb && k0 == 0 && k1 == 0;
+    if (!inb) return fwd;
+    const int kl0 = local_z(g, k0), kl1 = g.is3d ? local_z(g, k1) : kl0;
+#define TFL_MM(kk, jj, ii) { const float t = __ldg(orig_c + cell(g, kk, jj, ii)); if (t < lo) lo = t; if (t > hi) hi = t; }
+    TFL_MM(kl0, j0, i0) TFL_MM(kl0, j0, i1) TFL_MM(kl0, j1, i0) TFL_MM(kl0, j1, i1)
+    if (g.is3d) { TFL_MM(kl1, j0, i0) TFL_MM(kl1, j0, i1) TFL_MM(kl1, j1, i0) TFL_MM(kl1, j1, i1) }
+#undef TFL_MM
+  }
+  return clamp_f(val, lo, hi);
+}
+
+// Backward pass on the forward field + MacCormackCorrectMAC + MacCormackClampMAC, fused
+// (third_party/tfluids.cc:859-915, 660-774).
+template <bool OURS>
+__global__ void k_advect_vel_pass2(const float* __restrict__ U, const float* __restrict__ fwd,
+                                   const float* __restrict__ flags, float* __restrict__ dst, float dt,
+                                   float strength, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float* fl = flags + b * g.n;
+  const float* ub = U + (long long)b * g.nc * g.n;
+  const float* fb = fwd + (long long)b * g.nc * g.n;
+  const bool border = on_border(g, k, j, i);
+  V3 bw = {0.0f, 0.0f, 0.0f};
+  if (!border) bw = advect_mac_cell<OURS>(fl, ub, fb, g, -dt, k, j, i);
+  const int kg = k + g.zoff;
+  const bool cf = flag_i(fl, g, k, j, i) & kFluid;
+  bool skip[3] = {!cf, !cf, !cf};
+  if (i > 0 && !(flag_i(fl, g, k, j, i - 1) & kFluid)) skip[0] = true;
+  if (j > 0 && !(flag_i(fl, g, k, j - 1, i) & kFluid)) skip[1] = true;
+  if (g.is3d && kg > 0 && !(flag_i(fl, g, local_z(g, kg - 1), j, i) & kFluid)) skip[2] = true;
+  const float bwv[3] = {bw.x, bw.y, bw.z};
+  float val[3], fwv[3];
+  for (int a = 0; a < g.nc; a++) {
+    fwv[a] = __ldg(fb + a * g.n + c);
+    float v = fwv[a];
+    if (!skip[a]) {
+      const float diff = __ldg(ub + a * g.n + c) - bwv[a];
+      v = (float)((double)v + ((double)strength * 0.5) * (double)diff);
+    }
+    val[a] = v;
+  }
+  if (!border) {
+    val[0] = clamp_component_mac(ub, g, val[0], fwv[0], kg, j, i, scale3(mac_at_x(ub, g, k, j, i), dt));
+    val[1] = clamp_component_mac(ub + g.n, g, val[1], fwv[1], kg, j, i, scale3(mac_at_y(ub, g, k, j, i), dt));
+    if (g.is3d)
+      val[2] = clamp_component_mac(ub + 2 * g.n, g, val[2], fwv[2], kg, j, i,
+                                   scale3(mac_at_z(ub, g, k, j, i), dt));
+  }
+  float* db = dst + (long long)b * g.nc * g.n + c;
+  for (int a = 0; a < g.nc; a++) db[a * g.n] = val[a];
+}
+
+// ---------------------------------------------------------------------------------------
+// Jacobi.  The obstacle tests of the 7-point stencil are folded once per solve into one
+// byte per cell; iterations then read p(7) + div + 1 byte and stay bit-identical to
+// generic/tfluids.cu:1765-1821 in IEEE arithmetic.
+//   bit0: cell is border-or-obstacle (p = 0); bits1..6: neighbour -x,+x,-y,+y,-z,+z is obstacle.
+// ---------------------------------------------------------------------------------------
+__global__ void k_jacobi_mask(const float* __restrict__ flags, unsigned char* __restrict__ mask, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const float* fl = flags + b * g.n;
+  unsigned m = 0;
+  if (on_border(g, k, j, i) || (flag_i(fl, g, k, j, i) & kObstacle)) {
+    m = 1;
+  } else {
+    if (flag_i(fl, g, k, j, i - 1) & kObstacle) m |= 2;
+    if (flag_i(fl, g, k, j, i + 1) & kObstacle) m |= 4;
+    if (flag_i(fl, g, k, j - 1, i) & kObstacle) m |= 8;
+    if (flag_i(fl, g, k, j + 1, i) & kObstacle) m |= 16;
+    if (g.is3d) {
+      if (flag_i(fl, g, k - 1, j, i) & kObstacle) m |= 32;
+      if (flag_i(fl, g, k + 1, j, i) & kObstacle) m |= 64;
+    }
+  }
+  mask[b * g.n + cell(g, k, j, i)] = (unsigned char)m;
+}
+
+__global__ void k_jacobi_iter(const unsigned char* __restrict__ mask, const float* __restrict__ div,
+                              const float* __restrict__ prev, float* __restrict__ cur, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const long long c = b * g.n + cell(g, k, j, i);
+  const unsigned m = mask[c];
+  if (m & 1) { cur[c] = 0.0f; return; }
+  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const float pc = __ldg(prev + c);
+  float p1 = (m & 2) ? pc : __ldg(prev + c - 1);
+  float p2 = (m & 4) ? pc : __ldg(prev + c + 1);
+  float p3 = (m & 8) ? pc : __ldg(prev + c - sy);
+  float p4 = (m & 16) ? pc : __ldg(prev + c + sy);
+  float p5 = 0.0f, p6 = 0.0f;
+  if (g.is3d) {
+    p5 = (m & 32) ? pc : __ldg(prev + c - sz);
+    p6 = (m & 64) ? pc : __ldg(prev + c + sz);
+  }
+  const float denom = g.is3d ? 6.0f : 4.0f;
+  cur[c] = (p1 + p2 + p3 + p4 + p5 + p6 + __ldg(div + c)) / denom;
+}
+
+// sum over one batch element of (a - b)^2, accumulated in double: out[b] += ...
+__global__ void k_sqdiff(const float* __restrict__ a, const float* __restrict__ bb, long long n,
+                         double* __restrict__ out) {
+  const int b = blockIdx.y;
+  const float* pa = a + b * n;
+  const float* pb = bb + b * n;
+  double acc = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+       t += (long long)gridDim.x * blockDim.x) {
+    const float d = pa[t] - pb[t];
+    acc += (double)d * (double)d;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ double warp_sums[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    acc = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(out + b, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Flat element-wise helpers (the cutorch calls lib/simulate.lua makes on the step).
+// ---------------------------------------------------------------------------------------
+__global__ void k_apply_bc(float* __restrict__ x, const float* __restrict__ inv, const float* __restrict__ bc,
+                           long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float v = x[t] * __ldg(inv + t);
+  x[t] = v + __ldg(bc + t);
+}
+__global__ void k_clamp(float* __restrict__ x, float lo, float hi, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float v = x[t];
+  x[t] = (v < lo) ? lo : ((v > hi) ? hi : v);
+}
+
+// ---------------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------------
+#define TFL_LAUNCH3(kernel, g, st, ...)            \
+  do {                                             \
+    dim3 grid_, block_;                            \
+    launch_dims(g, grid_, block_);                 \
+    kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
+  } while (0)
+
+void launch_empty_domain(float* flags, const Geo& g, int bnd, cudaStream_t st) {
+  TFL_LAUNCH3(k_empty_domain, g, st, flags, g, bnd);
+}
+void launch_flags_to_occupancy(const float* flags, float* occ, long long n, unsigned long long* bad,
+                               cudaStream_t st) {
+  k_flags_to_occupancy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, occ, n, bad);
+}
+void launch_set_wall_bcs(float* U, const float* flags, const Geo& g, int as_mask, cudaStream_t st) {
+  TFL_LAUNCH3(k_set_wall_bcs, g, st, U, flags, g, as_mask);
+}
+void launch_divergence(const float* U, const float* flags, float* div, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_divergence, g, st, U, flags, div, g);
+}
+void launch_velocity_update(float* U, const float* flags, const float* p, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_velocity_update, g, st, U, flags, p, g);
+}
+void launch_add_buoyancy(float* U, const float* flags, const float* rho, const float s[3], const Geo& g,
+                         cudaStream_t st) {
+  TFL_LAUNCH3(k_add_buoyancy, g, st, U, flags, rho, s[0], s[1], s[2], g);
+}
+void launch_add_gravity(float* U, const float* flags, const float f[3], const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_add_gravity, g, st, U, flags, f[0], f[1], f[2], g);
+}
+int launch_vorticity(float* U, const float* flags, float strength, float* curl, float* cnorm, const Geo& g,
+                     cudaStream_t st) {
+  // curl / |curl| are needed one cell beyond the computed range in every direction
+  // (confinement force at i-1 reads |curl| at i-2): widen the first pass in z.
+  Geo g1 = g;
+  g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
+  g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
+  TFL_LAUNCH3(k_vort_curl, g1, st, U, curl, cnorm, g1);
+  TFL_LAUNCH3(k_vort_apply, g, st, U, flags, curl, cnorm, strength, g);
+  return 2;
+}
+
+int launch_advect_scalar(float dt, const float* s, const float* U, const float* flags, int method,
+                         int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
+                         const Geo& g_fwd, cudaStream_t st) {
+  switch (method) {
+    case TFL_ADVECT_EULER:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_EULER>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      return 1;
+    case TFL_ADVECT_EULER_OURS:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_EULER_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      return 1;
+    case TFL_ADVECT_RK2_OURS:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_RK2_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      return 1;
+    case TFL_ADVECT_RK3_OURS:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_RK3_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      return 1;
+    case TFL_ADVECT_MACCORMACK:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_MACCORMACK>, g_fwd, st, s, U, flags, fwd, nullptr, dt, outside, g_fwd);
+      TFL_LAUNCH3(k_advect_scalar_pass2_manta, g, st, s, fwd, U, flags, dst, dt, strength, g);
+      return 2;
+    case TFL_ADVECT_MACCORMACK_OURS:
+      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_MACCORMACK_OURS>, g_fwd, st, s, U, flags, fwd, fwd_pos, dt, outside, g_fwd);
+      TFL_LAUNCH3(k_advect_scalar_pass2_ours, g, st, s, fwd, fwd_pos, U, flags, dst, dt, strength, outside, g);
+      return 2;
+  }
+  return -1;
+}
+
+int launch_advect_vel(float dt, const float* U, const float* flags, int method, float strength, float* dst,
+                      float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st) {
+  if (method == TFL_ADVECT_RK2_OURS || method == TFL_ADVECT_RK3_OURS) method = TFL_ADVECT_MACCORMACK_OURS;
+  switch (method) {
+    case TFL_ADVECT_EULER:
+      TFL_LAUNCH3(k_advect_vel_pass1<false>, g, st, U, flags, dst, dt, g);
+      return 1;
+    case TFL_ADVECT_EULER_OURS:
+      TFL_LAUNCH3(k_advect_vel_pass1<true>, g, st, U, flags, dst, dt, g);
+      return 1;
+    case TFL_ADVECT_MACCORMACK:
+      TFL_LAUNCH3(k_advect_vel_pass1<false>, g_fwd, st, U, flags, fwd, dt, g_fwd);
+      TFL_LAUNCH3(k_advect_vel_pass2<false>, g, st, U, fwd, flags, dst, dt, strength, g);
+      return 2;
+    case TFL_ADVECT_MACCORMACK_OURS:
+      TFL_LAUNCH3(k_advect_vel_pass1<true>, g_fwd, st, U, flags, fwd, dt, g_fwd);
+      TFL_LAUNCH3(k_advect_vel_pass2<true>, g, st, U, fwd, flags, dst, dt, strength, g);
+      return 2;
+  }
+  return -1;
+}
+
+void launch_jacobi_mask(const float* flags, unsigned char* mask, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_jacobi_mask, g, st, flags, mask, g);
+}
+void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
+                        const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_jacobi_iter, g, st, mask, div, prev, cur, g);
+}
+void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st) {
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 592) blocks = 592;
+  k_sqdiff<<<dim3((unsigned)blocks, nb), 256, 0, st>>>(a, b, n, out);
+}
+void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, cudaStream_t st) {
+  k_apply_bc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, inv, bc, n);
+}
+void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st) {
+  k_clamp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, lo, hi, n);
+}
+
+}  // namespace tfl

@@ -1,0 +1,200 @@
+/*
+ * libtfl -- C ABI of the B200-native Eulerian fluid step (drop-in for the tfluids
+ * operators that FluidNet's `tfluids.simulate` calls).
+ *
+ * Every entry point replaces one reference `lua_CFunction` (registered in
+ * torch/tfluids/generic/tfluids.cu:1932-1953, wrapped by torch/tfluids/init.lua) or one
+ * cutorch tensor call that torch/lib/simulate.lua makes on the step.  Paths below are
+ * relative to /root/reference/torch/.
+ *
+ * Conventions
+ *  - All grids are float32, contiguous, 5-D [b][c][z][y][x] (x fastest), exactly the
+ *    layout the reference's Grid classes view (tfluids/third_party/grid.h:26-262):
+ *    flags / p / density / div have c == 1, U has c == 3 (3-D) or c == 2 (2-D, nz == 1).
+ *    `tfl_grid.data` is a DEVICE pointer owned by the caller (e.g. a LuaJIT cdata, a
+ *    torch tensor's data_ptr, or memory from tfl_alloc).  Nothing is retained across
+ *    calls except the context.
+ *  - Flags are float-encoded bit codes (tfluids/third_party/cell_type.h:22-33).
+ *  - Every function returns 0 on success, non-zero on error; tfl_last_error() gives the
+ *    message (the reference raises luaL_error / THError instead).
+ *  - A context is single-threaded; all work is enqueued on the context's stream and is
+ *    asynchronous unless stated.  Temporaries come from a context-owned arena (the
+ *    reference's Lua-side getTempStorage, tfluids/init.lua:35-64).
+ *  - There is no CPU fallback: without a CUDA device tfl_create fails.
+ *
+ * Slab decomposition (multi-GPU, no reference counterpart): a grid may be a z-slab of a
+ * larger global domain.  tfl_set_slab() tells the context where the local array sits in
+ * the global grid; border tests, getDx and line traces then use GLOBAL coordinates, as
+ * the single-GPU run would.
+ */
+#ifndef TFL_H_
+#define TFL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfl_ctx tfl_ctx;
+typedef struct tfl_cnn tfl_cnn;
+
+typedef struct tfl_grid {
+  float* data;                    /* device pointer */
+  int32_t nb, nc, nz, ny, nx;     /* sizes of the 5 dims */
+} tfl_grid;
+
+/* tfluids.CellType (tfluids/init.cu:108-124, third_party/cell_type.h:22-33). */
+enum {
+  TFL_CELL_NONE = 0, TFL_CELL_FLUID = 1, TFL_CELL_OBSTACLE = 2, TFL_CELL_EMPTY = 4,
+  TFL_CELL_INFLOW = 8, TFL_CELL_OUTFLOW = 16, TFL_CELL_OPEN = 32, TFL_CELL_STICK = 128
+};
+
+/* Advection methods, same order as AdvectMethod (tfluids/generic/advect_type.h:21-28);
+ * strings: "euler", "maccormack", "eulerOurs", "rk2Ours", "rk3Ours", "maccormackOurs"
+ * (advect_type.cc:19-38). */
+enum {
+  TFL_ADVECT_EULER = 0, TFL_ADVECT_MACCORMACK = 1, TFL_ADVECT_EULER_OURS = 2,
+  TFL_ADVECT_RK2_OURS = 3, TFL_ADVECT_RK3_OURS = 4, TFL_ADVECT_MACCORMACK_OURS = 5
+};
+int tfl_advect_method_from_string(const char* name);   /* -1 if unknown */
+
+/* ---- context ------------------------------------------------------------------------ */
+int tfl_create(tfl_ctx** out, int device);              /* fails without a CUDA device */
+void tfl_destroy(tfl_ctx* ctx);
+const char* tfl_last_error(const tfl_ctx* ctx);
+const char* tfl_version(void);
+/* Adopt an external cudaStream_t (e.g. torch's current stream); NULL = own stream.
+ * Replaces THCState_getCurrentStream (tfluids/generic/tfluids.cu:106,127). */
+int tfl_set_stream(tfl_ctx* ctx, void* cuda_stream);
+void* tfl_get_stream(tfl_ctx* ctx);
+int tfl_sync(tfl_ctx* ctx);
+/* Number of line traces since the last reset that hit a condition the reference CPU code
+ * treats as a hard error (generic/calc_line_trace.cc THError sites) or that left the
+ * local z-slab (halo too small).  Synchronises. */
+int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t tfl_launch_count(const tfl_ctx* ctx);
+
+/* z-slab placement of subsequent grids: local plane 0 is global plane `z_offset` of a
+ * domain with `global_nz` planes; operators compute local planes [z_lo, z_hi).
+ * tfl_set_slab(ctx, 0, 0, 0, 0) restores single-domain behaviour. */
+int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo, int32_t z_hi);
+
+/* ---- memory helpers (optional; callers may bring their own device pointers) ----------- */
+int tfl_alloc(tfl_ctx* ctx, size_t bytes, void** dev_ptr);
+int tfl_free(tfl_ctx* ctx, void* dev_ptr);
+int tfl_alloc_host(tfl_ctx* ctx, size_t bytes, void** pinned_host_ptr);
+int tfl_free_host(tfl_ctx* ctx, void* pinned_host_ptr);
+int tfl_memcpy_h2d(tfl_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);  /* async */
+int tfl_memcpy_d2h(tfl_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);  /* async */
+int tfl_memcpy_d2d(tfl_ctx* ctx, void* dev_dst, const void* dev_src, size_t bytes);   /* async */
+
+/* ---- operators (one per reference lua_CFunction) --------------------------------------- */
+/* tfluids.advectScalar (init.lua:89-149; CudaMain_advectScalar third_party/tfluids.cu:524-633;
+ * CPU third_party/tfluids.cc:415-588).  s_dst == NULL advects in place (init.lua:145-148).
+ * boundaryWidth is fixed to 1 as in the reference (third_party/tfluids.cc:436,467). */
+int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid* U,
+                      const tfl_grid* flags, int method, int sample_outside_fluid,
+                      float maccormack_strength, const tfl_grid* s_dst);
+/* tfluids.advectVel (init.lua:170-219; third_party/tfluids.cu:876-963; .cc:776-920). */
+int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* flags, int method,
+                   float maccormack_strength, const tfl_grid* U_dst);
+/* tfluids.setWallBcsForward (init.lua:228-247; third_party/tfluids.cu:969-1046). In place. */
+int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags);
+/* tfluids.velocityDivergenceForward (init.lua:256-279; third_party/tfluids.cu:1052-1105). */
+int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                                    const tfl_grid* div);
+/* tfluids.velocityUpdateForward (init.lua:324-349; third_party/tfluids.cu:1111-1195). In place. */
+int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                                const tfl_grid* p);
+/* tfluids.addBuoyancy (init.lua:442-471; third_party/tfluids.cu:1201-1273). gravity: 3 host floats. */
+int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                     const tfl_grid* density, const float gravity[3], float dt);
+/* tfluids.addGravity (init.lua:481-507; third_party/tfluids.cu:1279-1349). */
+int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                    const float gravity[3], float dt);
+/* tfluids.vorticityConfinement (init.lua:394-431; third_party/tfluids.cu:1355-1497). In place. */
+int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                              float strength);
+/* tfluids.solveLinearSystemJacobi (init.lua:693-734; generic/tfluids.cu:1765-1927).
+ * Synchronises once at the end to return the residual (the reference syncs every
+ * iteration, generic/tfluids.cu:1886). residual may be NULL (no sync then, if p_tol <= 0). */
+int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
+                                   const tfl_grid* div, int is_3d, float p_tol, int max_iter,
+                                   float* residual, int* iterations);
+/* tfluids.emptyDomain (init.lua:545-555; generic/tfluids.cu:314-353). */
+int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd);
+/* tfluids.flagsToOccupancy (init.lua:571-576; generic/tfluids.cu:355-401).  Cells that are
+ * neither Fluid nor Obstacle get -1 as in the CUDA reference; *bad_cells (may be NULL,
+ * synchronises if not) counts them so the host can raise like the CPU reference does. */
+int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* occupancy,
+                           int64_t* bad_cells);
+
+/* ---- cutorch tensor calls made by lib/simulate.lua on the step ------------------------ */
+/* x:cmul(inv_mask); x:add(bc)  (setConstVals, lib/simulate.lua:136-158). */
+int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc);
+/* U:clamp(lo, hi)  (lib/simulate.lua:326). */
+int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi);
+
+/* ---- CNN pressure projection (lib/model.lua:27-401, forward only) ---------------------- */
+/* Layer l is a stride-1, zero-padded ((k-1)/2) cross-correlation cin[l] -> cout[l] with a
+ * cubic (3-D) or square (2-D) kernel of edge ksize[l], bias, and ReLU after every layer
+ * but the last.  weights[l] is a HOST pointer to [cout][cin][kz][ky][kx] floats (Torch
+ * layout, kz == 1 in 2-D); biases[l] to [cout].  cin[0] must be 3 (pDiv, div, occupancy:
+ * the 'default' input set, lib/default_conf.lua:76-81) and cout[last] must be 1. */
+int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
+                   const int32_t* ksize, const float* const* weights, const float* const* biases,
+                   tfl_cnn** out);
+void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* cnn);
+/* model:forward({pDiv, UDiv, flags}) -> {p, U} (lib/model.lua:421-450).  threshold is
+ * mconf.normalizeInputThreshold (lib/default_conf.lua:106).  p_out / U_out may alias
+ * p_div / U_div.  scale_out (nb floats, HOST, may be NULL) synchronises if given. */
+int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* cnn, const tfl_grid* p_div, const tfl_grid* U_div,
+                    const tfl_grid* flags, const tfl_grid* p_out, const tfl_grid* U_out,
+                    float threshold, float* scale_out);
+
+/* ---- the whole step: tfluids.simulate (lib/simulate.lua:175-327) ----------------------- */
+typedef struct tfl_mconf {        /* keys the loop reads (lib/simulate.lua:188-291) */
+  float dt;
+  int32_t advection_method;       /* TFL_ADVECT_* */
+  float maccormack_strength;
+  double buoyancy_scale;          /* Lua numbers: the loop scales them in double */
+  double gravity_scale;
+  float gravity[3];               /* default (0, 1, 0), lib/simulate.lua:204-213 */
+  double vorticity_confinement_amp;
+  int32_t sim_method;             /* 0 convnet, 1 jacobi, 2 pcg */
+  int32_t max_iter;               /* <= 0: reference default (100) */
+  float normalize_input_threshold;
+} tfl_mconf;
+enum { TFL_SIM_CONVNET = 0, TFL_SIM_JACOBI = 1, TFL_SIM_PCG = 2 };
+
+typedef struct tfl_state {        /* the `batch` table; any BC pointer may be NULL */
+  tfl_grid p, U, flags, density;  /* density.data may be NULL */
+  tfl_grid U_bc, U_bc_inv_mask, density_bc, density_bc_inv_mask, p_bc, p_bc_inv_mask;
+  tfl_grid div;                   /* scratch for the non-convnet paths (batch.div) */
+} tfl_state;
+
+/* One call == one tfluids.simulate(conf, mconf, batch, model, false). Asynchronous.
+ * The operator sequence is fused into fewer kernels than the per-operator entry points
+ * use; results are identical to calling the operators one by one. */
+int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* state, const tfl_mconf* mconf, tfl_cnn* cnn);
+
+/* Same step through HOST buffers (what a host application holding CPU tensors calls):
+ * copies p, U, density in (pinned staging inside the context), runs the step, copies
+ * p, U, density back, and synchronises.  flags / BC arrays are uploaded by
+ * tfl_host_state_create once.  Used for the end-to-end number in bench.py. */
+typedef struct tfl_host_sim tfl_host_sim;
+int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_t nx, int is_3d,
+                        const float* flags, const float* U_bc, const float* U_bc_inv_mask,
+                        const float* density_bc, const float* density_bc_inv_mask,
+                        tfl_host_sim** out);
+void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs);
+int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
+                      const tfl_mconf* mconf, tfl_cnn* cnn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFL_H_ */

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- simulation steps/s of the Eulerian fluid step (BASELINE.json metric) on N B200s.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line (rank 0).
+One *step* = one `tfluids.simulate` call (torch/lib/simulate.lua:175-327) on a 128^3 MAC
+grid: MacCormack("maccormackOurs") advection of density and velocity, plume BCs, buoyancy,
+vorticity confinement and the CNN pressure projection -- BASELINE.json configs[2]
+(configs[1], 64^3 CNN forward only, is a parity-test case).
+
+  value     whole-job steps/s with the state resident in HBM (CUDA events on the launch stream)
+  e2e       the same step through the C-ABI host-buffer call (tfl_host_sim_step): pinned
+            host p/U/density copied in, step, copied back, every step
+  roofline  the dominant kernel's ALGORITHMIC bytes / its measured mean duration vs the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own CPU operators (oracle/_ref, compiled in place) -- or the C
+            restatement when that is absent -- timed on this box's host cores on a bounded
+            sample (one full 128^3 step without the conv stack is ~1 s on 8 cores; the sample
+            used is stated)
+
+`--impl reference` times that CPU path alone and prints the same line shape.
+Multi-GPU (N > 1, launched with torchrun): weak scaling -- every rank advances an
+independent 128^3 grid (the batch-of-grids decomposition north_star allows); no data-path
+collective; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 128
+# algorithmic bytes per voxel of one C3 step (fp32, flags as fp32).
+BYTES_PER_VOXEL_STEP = 364
+# dominant kernels' algorithmic bytes per voxel (DESIGN.md "Kernels"): filled per kernel name
+ALGO_BYTES = {
+    "advect_vel": 28,       # U 12 + flags 4 read, U 12 written   (both MacCormack passes)
+    "advect_scalar": 24,    # s 4 + U 12 + flags 4 read, s 4 written
+    "cnn": 36,              # pDiv 4 + UDiv 12 + flags 4 read, p 4 + U 12 written
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.stop_flag = threading.Event()
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                parts = [x.strip() for x in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for nm, v in zip(names, parts[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def make_problem(n=N_GRID):
+    from fluidnet_b200 import synth
+    import oracle  # noqa: F401  (only for the plume-BC builder shared with the tests)
+    flags = synth.make_flags(n, n, n, True, nb=1, geometry=True)
+    U = synth.make_smooth_velocity(flags, True, amp=2.0)
+    density = synth.make_density(flags)
+    batch = {"pDiv": np.zeros_like(flags), "UDiv": U, "flags": flags, "density": density}
+    from oracle.api import create_plume_bcs
+    create_plume_bcs(batch, [1.0], n / 128.0, 0.15)
+    # fluid_net_3d_sim.lua:73-87
+    mconf = dict(dt=0.1, advectionMethod="maccormackOurs", maccormackStrength=0.6,
+                 buoyancyScale=2.0 * n / 128.0, gravityScale=0.0, gravity=None,
+                 vorticityConfinementAmp=3.0, simMethod="convnet", maxIter=None, is3D=True,
+                 normalizeInputThreshold=1e-5)
+    return batch, mconf, synth.make_model(True)
+
+
+def cpu_step_ops(be, batch, mconf, with_cnn_model=None):
+    """One step with the CPU reference operators (conv stack optional: it is not reference
+    code, lib/model.lua's cuDNN layers have no CPU source in the tree)."""
+    import oracle
+    if with_cnn_model is not None:
+        oracle.simulate(be, mconf, batch, with_cnn_model)
+    else:
+        m = dict(mconf)
+        m["simMethod"] = "jacobi"
+        m["maxIter"] = 1
+        oracle.simulate(be, m, batch, None)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.build()
+    be = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
+    n = N_GRID
+    batch, mconf, mnp = make_problem(n)
+    # bounded sample: advection + forces + BCs + wall/divergence/1 Jacobi sweep/velocity update
+    # of the full 128^3 grid (everything the reference has CPU code for); the conv stack is
+    # excluded from the reference arm because its CPU source is not in the reference tree.
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cpu_step_ops(be, batch, mconf, None)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    T = float(np.mean(times))
+    v = 1.0 / T
+    line = {"impl": "reference", "metric": "sim steps/sec on 128^3 MAC grid (CNN proj)", "value": v,
+            "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "3D 128^3 MAC grid, maccormackOurs advection + buoyancy + vorticity "
+                                   "confinement + projection", "grid": [n, n, n]},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": be.num_threads(),
+                             "kind": "reference" if be.name == "reference" else "port",
+                             "sample": "full 128^3 step of the reference CPU operators; the CNN conv stack "
+                                       "(no CPU source in the reference) replaced by 1 Jacobi sweep"},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--grid", type=int, default=N_GRID)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from fluidnet_b200 import tfluids, simulate, model as fmodel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.grid
+    batch_np, mconf, mnp = make_problem(n)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        gb = {k: torch.from_numpy(v.copy()).cuda() for k, v in batch_np.items()}
+        gm = fmodel.ProjectionModel(mnp["layers"], True)
+        ctx = tfluids.context()
+        # L2 flush buffer (> 126 MB) written between timed iterations.
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+        def step():
+            simulate.simulate_fused(None, mconf, gb, gm)
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.launch_count()
+        evs = []
+        for _ in range(args.steps):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+            evs.append((e0, e1))
+        stream.synchronize()
+        torch.cuda.synchronize()
+        launches = ctx.launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            sampler.stop_flag.set()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = t.item()
+        assert ctx.trace_faults() == 0, "line traces left the domain / hit a hard-error path"
+
+        # ---- e2e: host buffers through the C-ABI host-sim call -----------------------------
+        import ctypes as C
+        lib = ctx.lib
+        hs = C.c_void_p()
+        fl = np.ascontiguousarray(batch_np["flags"])
+        arrs = [np.ascontiguousarray(batch_np[k]) for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask")]
+        ctx.check(lib.tfl_host_sim_create(ctx.h, 1, n, n, n, 1, fl.ctypes.data, arrs[0].ctypes.data,
+                                          arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data,
+                                          C.byref(hs)))
+        hp = torch.zeros(1, 1, n, n, n).pin_memory()
+        hU = torch.from_numpy(batch_np["UDiv"].copy()).pin_memory()
+        hd = torch.from_numpy(batch_np["density"].copy()).pin_memory()
+        mc = simulate.make_mconf(mconf)
+        e2e_steps = max(3, min(args.steps, 20))
+        for _ in range(2):
+            ctx.check(lib.tfl_host_sim_step(ctx.h, hs, hp.data_ptr(), hU.data_ptr(), hd.data_ptr(), C.byref(mc), gm.h))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.check(lib.tfl_host_sim_step(ctx.h, hs, hp.data_ptr(), hU.data_ptr(), hd.data_ptr(), C.byref(mc), gm.h))
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+        lib.tfl_host_sim_destroy(ctx.h, hs)
+        bytes_io = 5 * n ** 3 * 4
+
+        # ---- roofline of the dominant kernel (advectVel, both passes), timed alone --------
+        peak, peak_src = peaks()
+        U = gb["UDiv"]
+        Ud = torch.empty_like(U)
+        reps = 10
+        for _ in range(3):
+            tfluids.advectVel(0.1, U, gb["flags"], "maccormackOurs", Ud, 0.6)
+        ks = []
+        for _ in range(reps):
+            flush.fill_(0.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            tfluids.advectVel(0.1, U, gb["flags"], "maccormackOurs", Ud, 0.6)
+            b.record(stream)
+            ks.append((a, b))
+        stream.synchronize()
+        k_ms = float(np.mean([a.elapsed_time(b) for a, b in ks]))
+        algo_bytes = ALGO_BYTES["advect_vel"] * n ** 3
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        be = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
+        b2, m2, _ = make_problem(n)
+        t0 = time.perf_counter()
+        cpu_step_ops(be, b2, m2, None)
+        t1 = time.perf_counter() - t0
+        cpu = {"value": 1.0 / t1, "unit": "steps/s", "cores": be.num_threads(),
+               "kind": "reference" if be.name == "reference" else "port",
+               "sample": "1 full %d^3 step of the reference CPU operators (advection, BCs, buoyancy, "
+                         "vorticity, wall BCs, divergence, velocity update; CNN conv stack replaced by 1 "
+                         "Jacobi sweep: no CPU conv source in the reference)" % n}
+
+    ms = total_ms / args.steps
+    line = {
+        "metric": "sim steps/sec on 128^3 MAC grid (CNN proj)",
+        "value": world * 1000.0 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D %d^3 MAC grid per GPU, maccormackOurs advection (density+velocity) + plume "
+                               "BCs + buoyancy + vorticity confinement + CNN projection (3-D default net), "
+                               "1 tfluids.simulate per step" % n,
+                   "grid": [n, n, n], "batch_per_gpu": 1, "parallelism": "independent grid per GPU",
+                   "l2": "256 MB buffer written between timed steps (L2 flush)"},
+        "hbm_gbs_algorithmic": BYTES_PER_VOXEL_STEP * n ** 3 / (ms * 1e-3) / 1e9,
+        "e2e": {"value": world * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": bytes_io,
+                "d2h_bytes_per_step": bytes_io},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "advectVel (k_advect_vel_pass1+pass2, maccormackOurs)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

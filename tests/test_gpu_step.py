@@ -1,0 +1,149 @@
+"""Whole-step parity: tfluids.simulate (torch/lib/simulate.lua:175-327) on the GPU, both
+operator-by-operator (fluidnet_b200.simulate.simulate) and through the single C-ABI call
+(tfl_simulate_step), against the oracle's restatement of the same loop.
+
+Tolerances
+  * jacobi path (no conv): bit-exact -- every kernel is a per-cell restatement built
+    without FMA contraction.
+  * convnet path: the conv stack accumulates in fp32 FMA on the GPU and in fp64 in the
+    oracle (the reference used cuDNN, algorithm unspecified): |err| <= 2e-5 * max|field|
+    after one step, the reference's own cross-backend tolerance class (1e-5 abs on O(1)
+    data, test_tfluids.lua:34).  The input scale (sample std) is a reduction: 1e-5 rel."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from cases import bits_equal, describe_diff
+from fluidnet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(n, is3d, plume=True, geometry=True, amp=3.0):
+    nz = n if is3d else 1
+    flags = synth.make_flags(n, n, nz, is3d, nb=1, geometry=geometry)
+    U = synth.make_smooth_velocity(flags, is3d, amp=amp)
+    oracle.Oracle().setWallBcsForward(U, flags)
+    batch = {"pDiv": np.zeros_like(flags), "UDiv": U, "flags": flags, "density": synth.make_density(flags)}
+    if plume:
+        oracle.create_plume_bcs(batch, [1.0], n / 128.0 * 4, 0.15)
+    return batch
+
+
+def to_gpu(batch):
+    return {k: torch.from_numpy(v.copy()).cuda() for k, v in batch.items() if v is not None}
+
+
+def close(got, want, tol, what):
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64)).max()
+    scale = max(np.abs(want).max(), 1e-6)
+    assert err <= tol * scale, "%s: max err %g vs scale %g" % (what, err, scale)
+
+
+@pytest.mark.parametrize("is3d,n", [(False, 64), (True, 20)], ids=["2d64", "3d20"])
+@pytest.mark.parametrize("fused", [False, True], ids=["ops", "fused"])
+def test_step_jacobi_bit_exact(orc, is3d, n, fused):
+    """BASELINE config 1: 2-D 64x64 smoke, Jacobi projection, 1 step (and a small 3-D one)."""
+    from fluidnet_b200 import simulate
+    batch = make_batch(n, is3d)
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=1.0,
+                                 vorticityConfinementAmp=(0.0 if not is3d else 3.0),
+                                 simMethod="jacobi", maxIter=100, is3D=is3d)
+    gb = to_gpu(batch)
+    for step in range(2):
+        (simulate.simulate_fused if fused else simulate.simulate)(None, mconf, gb, None)
+        oracle.simulate(orc, mconf, batch, None)
+        for k in ("density", "UDiv", "pDiv"):
+            got = gb[k].cpu().numpy()
+            assert bits_equal(got, batch[k]), "step %d %s: %s" % (step, k, describe_diff(got, batch[k]))
+
+
+@pytest.mark.parametrize("is3d,n", [(True, 24), (False, 48)], ids=["3d24", "2d48"])
+def test_cnn_projection_forward(orc, is3d, n):
+    """BASELINE config 2 (shape-reduced for the CPU oracle): model:forward only."""
+    from gpu_backend import make_gpu_model
+    batch = make_batch(n, is3d, plume=False)
+    mnp = synth.make_model(is3d)
+    p0 = (synth.make_density(batch["flags"], seed=77) - np.float32(0.5)) * np.float32(0.1)
+    wp, wU, wscale = oracle.model_forward(orc, mnp, p0, batch["UDiv"], batch["flags"])
+    gm = make_gpu_model(mnp)
+    gp, gU = gm.forward((torch.from_numpy(p0).cuda(), torch.from_numpy(batch["UDiv"]).cuda(),
+                         torch.from_numpy(batch["flags"]).cuda()), return_scale=True)
+    assert abs(gm.last_scale[0] - wscale[0]) <= 1e-5 * wscale[0]
+    close(gp.cpu().numpy(), wp, 2e-5, "p")
+    close(gU.cpu().numpy(), wU, 2e-5, "U")
+    # occupancy / wall logic is exact: every face the oracle zeroes is exactly zero here.
+    assert np.array_equal(gU.cpu().numpy() == 0, wU == 0)
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["ops", "fused"])
+def test_step_convnet(orc, fused):
+    """BASELINE config 3 shape-reduced: CNN projection + vorticity confinement + MacCormack."""
+    from fluidnet_b200 import simulate
+    from gpu_backend import make_gpu_model
+    n = 24
+    batch = make_batch(n, True)
+    mnp = synth.make_model(True)
+    gm = make_gpu_model(mnp)
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=2.0 * n / 128,
+                                 vorticityConfinementAmp=3.0, simMethod="convnet")
+    gb = to_gpu(batch)
+    for step in range(2):
+        (simulate.simulate_fused if fused else simulate.simulate)(None, mconf, gb, gm)
+        oracle.simulate(orc, mconf, batch, mnp)
+        tol = 2e-5 if step == 0 else 2e-4          # second step: advection of slightly different fields
+        for k in ("density", "UDiv", "pDiv"):
+            close(gb[k].cpu().numpy(), batch[k], tol, "step %d %s" % (step, k))
+
+
+def test_fused_equals_operator_sequence():
+    """tfl_simulate_step must equal calling the operators one by one (bitwise)."""
+    from fluidnet_b200 import simulate
+    from gpu_backend import make_gpu_model
+    n = 32
+    batch = make_batch(n, True)
+    gm = make_gpu_model(synth.make_model(True))
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=0.5,
+                                 vorticityConfinementAmp=3.0, simMethod="convnet")
+    a, b = to_gpu(batch), to_gpu(batch)
+    for _ in range(3):
+        simulate.simulate(None, mconf, a, gm)
+        simulate.simulate_fused(None, mconf, b, gm)
+    for k in ("density", "UDiv", "pDiv"):
+        # the only non-deterministic piece is the double-precision atomic sum behind the
+        # input scale; allow 1 ulp-class differences there.
+        close(a[k].cpu().numpy(), b[k].cpu().numpy(), 1e-6, k)
+
+
+def test_full_size_properties():
+    """BASELINE-size (128^3) checks that do not need the CPU oracle: the Jacobi-projected
+    velocity is (nearly) divergence free, the obstacle faces stay exactly zero, advection of
+    a constant field is the identity in the fluid interior, and nothing traces out of bounds."""
+    from fluidnet_b200 import tfluids
+    n = 128
+    flags_np = synth.make_flags(n, n, n, True, nb=1, geometry=True)
+    flags = torch.from_numpy(flags_np).cuda()
+    U = torch.from_numpy(synth.make_smooth_velocity(flags_np, True, amp=4.0)).cuda()
+    tfluids.setWallBcsForward(U, flags)
+    ones = torch.where(flags == 1, 1.0, 0.0).contiguous()
+    adv = torch.empty_like(ones)
+    tfluids.advectScalar(0.1, ones, U, flags, "maccormackOurs", adv, False, 0.6)
+    interior = torch.zeros_like(flags, dtype=torch.bool)
+    interior[..., 1:-1, 1:-1, 1:-1] = True
+    fluid_in = (flags == 1) & interior
+    assert torch.all(adv[fluid_in] == 1.0)           # interpolating only fluid cells of a constant
+    div = torch.empty_like(flags)
+    tfluids.velocityDivergenceForward(U, flags, div)
+    d0 = div.abs().max().item()
+    p = torch.zeros_like(flags)
+    tfluids.solveLinearSystemJacobi(p, flags, div, True, 0, 2000)
+    tfluids.velocityUpdateForward(U, flags, p)
+    tfluids.setWallBcsForward(U, flags)
+    tfluids.velocityDivergenceForward(U, flags, div)
+    assert div.abs().max().item() < 0.2 * d0
+    # idempotence of the wall BCs
+    U2 = U.clone()
+    tfluids.setWallBcsForward(U2, flags)
+    assert torch.equal(U, U2)
+    assert tfluids.context().trace_faults() == 0
