@@ -38,7 +38,7 @@ SYMBOLS = [
     "tfl_set_wall_bcs_forward", "tfl_velocity_divergence_forward", "tfl_velocity_update_forward",
     "tfl_add_buoyancy", "tfl_add_gravity", "tfl_vorticity_confinement",
     "tfl_solve_linear_system_jacobi", "tfl_empty_domain", "tfl_flags_to_occupancy", "tfl_apply_bc",
-    "tfl_clamp", "tfl_cnn_create", "tfl_cnn_destroy", "tfl_cnn_project", "tfl_simulate_step",
+    "tfl_clamp", "tfl_cnn_create", "tfl_cnn_destroy", "tfl_cnn_set_mode", "tfl_cnn_get_mode", "tfl_cnn_project", "tfl_simulate_step",
     "tfl_host_sim_create", "tfl_host_sim_destroy", "tfl_host_sim_step",
 ]
 
@@ -88,6 +88,8 @@ def load():
                                    C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)),
                                    C.POINTER(C.c_void_p)]
     lib.tfl_cnn_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tfl_cnn_set_mode.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.tfl_cnn_get_mode.argtypes = [C.c_void_p]
     lib.tfl_cnn_project.argtypes = [C.c_void_p, C.c_void_p, G, G, G, G, G, C.c_float,
                                     C.POINTER(C.c_float)]
     lib.tfl_simulate_step.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(MConf), C.c_void_p]

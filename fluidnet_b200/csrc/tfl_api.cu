@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "tfl_kernels.h"
+#include "tfl_cnn_tc.h"
 
 using namespace tfl;
 
@@ -37,6 +38,13 @@ struct tfl_cnn {
   std::vector<float*> w;     // device, [cin][tap][cout]
   std::vector<float*> b;     // device, [cout]
   int max_c = 0;
+  // tensor-core path (3-D 'default' architecture only)
+  int mode = 0;              // 0 fp32 FMA, 1 TF32 tensor cores, 2 3xTF32 tensor cores
+  bool tc_ok = false;
+  float* wB[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [split][layer]
+  float* tail = nullptr;     // w4[8][8], b4[8], w5[8], b5[1]
+  float* act[3] = {nullptr, nullptr, nullptr};   // padded channels-last activation buffers
+  ConvTcGeo act_geo = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -531,15 +539,52 @@ int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, co
     m->w.push_back(dw); m->b.push_back(db);
     if (cout[l] > m->max_c) m->max_c = cout[l];
   }
+  // Tensor-core eligibility: the 3-D 'default' graph (lib/model.lua:219-226).
+  static const int want[5][3] = {{3, 8, 3}, {8, 8, 3}, {8, 8, 3}, {8, 8, 1}, {8, 1, 1}};
+  m->tc_ok = is_3d && n_layers == 5;
+  for (int l = 0; m->tc_ok && l < 5; l++)
+    m->tc_ok = cin[l] == want[l][0] && cout[l] == want[l][1] && ksize[l] == want[l][2];
+  if (m->tc_ok) {
+    for (int split = 0; split < 2; split++)
+      for (int l = 0; l < 3; l++) {
+        std::vector<float> packed(conv_tc_b_floats(split));
+        conv_tc_pack_weights(weights[l], cin[l], split, packed.data());
+        cudaMalloc((void**)&m->wB[split][l], packed.size() * 4);
+        cudaMemcpy(m->wB[split][l], packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
+      }
+    std::vector<float> tail(64 + 8 + 8 + 1);
+    memcpy(tail.data(), weights[3], 64 * 4);
+    memcpy(tail.data() + 64, biases[3], 8 * 4);
+    memcpy(tail.data() + 72, weights[4], 8 * 4);
+    tail[80] = biases[4][0];
+    cudaMalloc((void**)&m->tail, tail.size() * 4);
+    cudaMemcpy(m->tail, tail.data(), tail.size() * 4, cudaMemcpyHostToDevice);
+    m->mode = 2;
+  }
   *out = m;
   return 0;
 }
+
+int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
+  if (!m || mode < 0 || mode > 2) return fail(ctx, "cnn_set_mode: bad arguments");
+  if (mode > 0 && !m->tc_ok)
+    return fail(ctx, "cnn_set_mode: the tensor-core path covers the 3-D 'default' architecture only");
+  m->mode = mode;
+  return 0;
+}
+int tfl_cnn_get_mode(const tfl_cnn* m) { return m ? m->mode : -1; }
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   if (!m) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (float* p : m->w) cudaFree(p);
   for (float* p : m->b) cudaFree(p);
+  for (int sp = 0; sp < 2; sp++)
+    for (int l = 0; l < 3; l++)
+      if (m->wB[sp][l]) cudaFree(m->wB[sp][l]);
+  if (m->tail) cudaFree(m->tail);
+  for (float* p : m->act)
+    if (p) cudaFree(p);
   delete m;
 }
 
@@ -560,6 +605,31 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
   launch_cnn_mask_stats(U_div, flags, U1, sums, g, st);
   launch_cnn_scale(sums, scale, g.nb, (long long)g.nc * g.n, threshold, st);
+  if (m->mode > 0 && m->tc_ok && !ctx->slab) {
+    // Tensor-core path: padded channels-last activations owned by the model (their zero
+    // borders must survive between calls, so they do not live in the shared arena).
+    if (m->act_geo.nb != g.nb || m->act_geo.nz != g.nz || m->act_geo.ny != g.ny || m->act_geo.nx != g.nx) {
+      TFL_CUDA(ctx, cudaStreamSynchronize(st));
+      m->act_geo = make_conv_tc_geo(g.nb, g.nz, g.ny, g.nx);
+      for (int i = 0; i < 3; i++) {
+        if (m->act[i]) cudaFree(m->act[i]);
+        m->act[i] = nullptr;
+        TFL_CUDA(ctx, cudaMalloc((void**)&m->act[i], conv_tc_act_bytes(m->act_geo)));
+        TFL_CUDA(ctx, cudaMemset(m->act[i], 0, conv_tc_act_bytes(m->act_geo)));
+      }
+    }
+    const ConvTcGeo& tg = m->act_geo;
+    const int split = m->mode == 2 ? 1 : 0;
+    launch_cnn_inputs_padded(p_div, U1, flags, scale, m->act[0], tg.px, tg.py, g, st);
+    launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
+    launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
+    float* p_net = actA;      // plain [b][z][y][x]
+    launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+    launch_cnn_finish(p_net, U1, flags, scale, p_out, U_out, g, st);
+    ctx->launches += 7;
+    if (scale_dev_out) *scale_dev_out = scale;
+    return check_launch(ctx, "cnn_project (tensor cores)");
+  }
   launch_cnn_inputs(p_div, U1, flags, scale, x0, g, st);
   ctx->launches += 3;
   const float* in = x0;

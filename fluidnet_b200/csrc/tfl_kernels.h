@@ -39,6 +39,8 @@ void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_
                       cudaStream_t st);
 void launch_cnn_inputs(const float* p_div, const float* U1, const float* flags, const float* scale,
                        float* x0, const Geo& g, cudaStream_t st);
+void launch_cnn_inputs_padded(const float* p_div, const float* U1, const float* flags, const float* scale,
+                              float* x0, int px, int py, const Geo& g, cudaStream_t st);
 void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, const float* scale,
                        float* p_out, float* U_out, const Geo& g, cudaStream_t st);
 

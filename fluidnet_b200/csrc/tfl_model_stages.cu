@@ -134,6 +134,28 @@ __global__ void k_cnn_inputs(const float* __restrict__ p_div, const float* __res
   xb[2 * g.n] = (f == kFluid) ? 0.0f : ((f == kObstacle) ? 1.0f : -1.0f);
 }
 
+// Same three input channels written as the first channels-last float4 plane of the padded
+// activation layout the tensor-core convolution reads (tfl_cnn_tc.cu): (pDiv/s, div/s, occ, 0).
+__global__ void k_cnn_inputs_padded(const float* __restrict__ p_div, const float* __restrict__ U1,
+                                    const float* __restrict__ flags, const float* __restrict__ scale,
+                                    float4* __restrict__ x0, int px, int py, Geo g) {
+  int b, k, j, i;
+  if (!thread_cell2(g, b, k, j, i)) return;
+  const long long c = cell(g, k, j, i);
+  const float sc = __ldg(scale + b);
+  const float* ub = U1 + (long long)b * g.nc * g.n;
+  const int f = flag_i(flags + b * g.n, g, k, j, i);
+  float dv = 0.0f;
+  if (!on_border(g, k, j, i) && (f & kFluid)) {
+    dv = __ldg(ub + c) - __ldg(ub + c + 1) + __ldg(ub + g.n + c) - __ldg(ub + g.n + c + g.nx);
+    if (g.is3d) dv += (__ldg(ub + 2 * g.n + c) - __ldg(ub + 2 * g.n + c + (long long)g.nx * g.ny));
+  }
+  const long long plane = (long long)(g.nz + 2) * py * px;
+  const long long o = (long long)b * 2 * plane + ((long long)(k + 1) * py + (j + 1)) * px + (i + 1);
+  x0[o] = make_float4(__ldg(p_div + b * g.n + c) / sc, dv / sc,
+                      (f == kFluid) ? 0.0f : ((f == kObstacle) ? 1.0f : -1.0f), 0.0f);
+}
+
 // U = setWallBcs(velocityUpdate(U1 / scale, p_net) * scale);  p = p_net * scale.
 __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __restrict__ U1,
                              const float* __restrict__ flags, const float* __restrict__ scale,
@@ -196,6 +218,10 @@ void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_
 void launch_cnn_inputs(const float* p_div, const float* U1, const float* flags, const float* scale,
                        float* x0, const Geo& g, cudaStream_t st) {
   TFL_LAUNCH3B(k_cnn_inputs, g, st, p_div, U1, flags, scale, x0, g);
+}
+void launch_cnn_inputs_padded(const float* p_div, const float* U1, const float* flags, const float* scale,
+                              float* x0, int px, int py, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3B(k_cnn_inputs_padded, g, st, p_div, U1, flags, scale, (float4*)x0, px, py, g);
 }
 void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, const float* scale,
                        float* p_out, float* U_out, const Geo& g, cudaStream_t st) {

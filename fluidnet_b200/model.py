@@ -49,6 +49,16 @@ class ProjectionModel:
         self.h = h
         self.last_scale = None
 
+    MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
+
+    def set_mode(self, mode):
+        """'fp32' (CUDA-core FMA), 'tf32' or 'tf32x3' (tcgen05 tensor cores)."""
+        self.ctx.check(self.ctx.lib.tfl_cnn_set_mode(self.ctx.h, self.h, self.MODES[mode]))
+
+    def get_mode(self):
+        m = self.ctx.lib.tfl_cnn_get_mode(self.h)
+        return [k for k, v in self.MODES.items() if v == m][0]
+
     def __del__(self):
         try:
             if getattr(self, "h", None):

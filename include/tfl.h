@@ -148,6 +148,11 @@ int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, co
                    const int32_t* ksize, const float* const* weights, const float* const* biases,
                    tfl_cnn** out);
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* cnn);
+/* Arithmetic of the convolution stack: 0 = fp32 FMA on the CUDA cores; 1 = TF32 tensor cores
+ * (tcgen05, fp32 accumulate); 2 = 3xTF32 tensor cores (error-compensated split, fp32-class
+ * accuracy; the default where available).  Modes 1 and 2 cover the 3-D 'default' architecture. */
+int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* cnn, int mode);
+int tfl_cnn_get_mode(const tfl_cnn* cnn);
 /* model:forward({pDiv, UDiv, flags}) -> {p, U} (lib/model.lua:421-450).  threshold is
  * mconf.normalizeInputThreshold (lib/default_conf.lua:106).  p_out / U_out may alias
  * p_div / U_div.  scale_out (nb floats, HOST, may be NULL) synchronises if given. */
