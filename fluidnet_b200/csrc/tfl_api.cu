@@ -588,6 +588,21 @@ void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   delete m;
 }
 
+// Tensor-core path: padded channels-last activations owned by the model (their zero borders
+// must survive between calls, so they do not live in the shared arena).
+static int cnn_ensure_act(tfl_ctx* ctx, tfl_cnn* m, const Geo& g) {
+  if (m->act_geo.nb == g.nb && m->act_geo.nz == g.nz && m->act_geo.ny == g.ny && m->act_geo.nx == g.nx) return 0;
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->act_geo = make_conv_tc_geo(g.nb, g.nz, g.ny, g.nx);
+  for (int i = 0; i < 3; i++) {
+    if (m->act[i]) cudaFree(m->act[i]);
+    m->act[i] = nullptr;
+    TFL_CUDA(ctx, cudaMalloc((void**)&m->act[i], conv_tc_act_bytes(m->act_geo)));
+    TFL_CUDA(ctx, cudaMemset(m->act[i], 0, conv_tc_act_bytes(m->act_geo)));
+  }
+  return 0;
+}
+
 static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const float* U_div,
                             const float* flags, float* p_out, float* U_out, float threshold, const Geo& g,
                             char* scratch, float** scale_dev_out) {
@@ -606,18 +621,7 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   launch_cnn_mask_stats(U_div, flags, U1, sums, g, st);
   launch_cnn_scale(sums, scale, g.nb, (long long)g.nc * g.n, threshold, st);
   if (m->mode > 0 && m->tc_ok && !ctx->slab) {
-    // Tensor-core path: padded channels-last activations owned by the model (their zero
-    // borders must survive between calls, so they do not live in the shared arena).
-    if (m->act_geo.nb != g.nb || m->act_geo.nz != g.nz || m->act_geo.ny != g.ny || m->act_geo.nx != g.nx) {
-      TFL_CUDA(ctx, cudaStreamSynchronize(st));
-      m->act_geo = make_conv_tc_geo(g.nb, g.nz, g.ny, g.nx);
-      for (int i = 0; i < 3; i++) {
-        if (m->act[i]) cudaFree(m->act[i]);
-        m->act[i] = nullptr;
-        TFL_CUDA(ctx, cudaMalloc((void**)&m->act[i], conv_tc_act_bytes(m->act_geo)));
-        TFL_CUDA(ctx, cudaMemset(m->act[i], 0, conv_tc_act_bytes(m->act_geo)));
-      }
-    }
+    if (cnn_ensure_act(ctx, m, g)) return 1;
     const ConvTcGeo& tg = m->act_geo;
     const int split = m->mode == 2 ? 1 : 0;
     launch_cnn_inputs_padded(p_div, U1, flags, scale, m->act[0], tg.px, tg.py, g, st);
@@ -690,6 +694,84 @@ static int set_const_vals(tfl_ctx* ctx, const tfl_state* s) {       // lib/simul
   return 0;
 }
 
+// Fused pipeline for the convnet path with the tensor-core conv stack: 12 launches, every
+// field crosses memory once per stage.  Bit-identical to the operator sequence below.
+static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl_cnn* m, const Geo& g) {
+  const size_t cells = (size_t)g.n * g.nb;
+  const bool has_density = s->density.data != nullptr;
+  if (cnn_ensure_act(ctx, m, g)) return 1;
+  if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4, cells * 4 * g.nc, cells * 4 * g.nc,
+                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb})))
+    return 1;
+  Carver cv(ctx);
+  float* fwd_s = cv.take<float>(cells);
+  float* fwd_pos = cv.take<float>(cells * g.nc);
+  float* tmp_s = cv.take<float>(cells);
+  float* fwd_u = cv.take<float>(cells * g.nc);
+  float* tmp_u = cv.take<float>(cells * g.nc);
+  float* curl = cv.take<float>(cells * 3);
+  float* cnorm = cv.take<float>(cells);
+  float* p_net = cv.take<float>(cells);
+  float* scale = cv.take<float>(g.nb);
+  cudaStream_t st = ctx->stream;
+  if (has_density) {
+    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, s->flags.data, mc->advection_method, 0,
+                                        mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, st);
+    if (nl < 0) return fail(ctx, "advectScalar: bad method");
+    ctx->launches += nl;
+  }
+  {
+    const int nl = launch_advect_vel(mc->dt, s->U.data, s->flags.data, mc->advection_method,
+                                     mc->maccormack_strength, tmp_u, fwd_u, g, g, st);
+    if (nl < 0) return fail(ctx, "advectVel: bad method");
+    ctx->launches += nl;
+  }
+  const int dmax = std::max(g.nx, std::max(g.ny, g.gnz));
+  const double dx = 1.0 / (double)dmax;
+  const bool u_bc = s->U_bc.data && s->U_bc_inv_mask.data;
+  const bool d_bc = has_density && s->density_bc.data && s->density_bc_inv_mask.data;
+  float bs[3] = {0.0f, 0.0f, 0.0f};
+  const int do_buoy = has_density && mc->buoyancy_scale > 0.0;
+  if (do_buoy) {
+    const float k = (float)(-(dx / 4.0) * mc->buoyancy_scale);
+    const float scale_dt = mc->dt / get_dx(g);
+    for (int a = 0; a < 3; a++) bs[a] = (-(mc->gravity[a] * k)) * scale_dt;
+  }
+  launch_post_advect(has_density ? tmp_s : nullptr, tmp_u, s->flags.data, has_density ? s->density.data : nullptr,
+                     s->U.data, u_bc ? s->U_bc_inv_mask.data : nullptr, u_bc ? s->U_bc.data : nullptr,
+                     d_bc ? s->density_bc_inv_mask.data : nullptr, d_bc ? s->density_bc.data : nullptr, do_buoy, bs,
+                     g, st);
+  ctx->launches += 1;
+  if (mc->gravity_scale > 0.0) {
+    const float k = (float)((-dx / 4.0) * mc->gravity_scale);
+    const float scale_dt = mc->dt / get_dx(g);
+    const float f[3] = {(mc->gravity[0] * k) * scale_dt, (mc->gravity[1] * k) * scale_dt, (mc->gravity[2] * k) * scale_dt};
+    launch_add_gravity(s->U.data, s->flags.data, f, g, st);
+    ctx->launches += 1;
+  }
+  const int do_vort = mc->vorticity_confinement_amp > 0.0;
+  const float amp = (float)(dx * mc->vorticity_confinement_amp);
+  if (do_vort) {
+    launch_vort_curl(s->U.data, curl, cnorm, g, st);
+    ctx->launches += 1;
+  }
+  double* sums = ctx->dscratch + 64;
+  TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
+  launch_vort_bc_mask(s->U.data, s->flags.data, curl, cnorm, do_vort, amp, u_bc ? s->U_bc_inv_mask.data : nullptr,
+                      u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
+  const ConvTcGeo& tg = m->act_geo;
+  const int split = m->mode == 2 ? 1 : 0;
+  launch_cnn_inputs_fused(s->p.data, s->U.data, s->flags.data, sums, mc->normalize_input_threshold, scale, m->act[0],
+                          tg.px, tg.py, g, st);
+  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
+  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
+  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+  launch_cnn_finish_fused(p_net, s->U.data, s->flags.data, scale, s->p.data, u_bc ? s->U_bc_inv_mask.data : nullptr,
+                          u_bc ? s->U_bc.data : nullptr, -1e6f, 1e6f, g, st);
+  ctx->launches += 6;
+  return check_launch(ctx, "simulate_step (fused)");
+}
+
 int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl_cnn* cnn) {
   if (!s || !mc) return fail(ctx, "simulate: nil state / mconf");
   if (check_scalar(ctx, &s->flags, "flags") || check_scalar(ctx, &s->p, "pDiv") || check_vel(ctx, &s->U, &s->flags))
@@ -698,6 +780,12 @@ int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl
   Geo g;
   if (make_geo(ctx, &s->flags, is3d, &g)) return 1;
   const bool has_density = s->density.data != nullptr;
+  if (mc->sim_method == TFL_SIM_CONVNET && cnn && cnn->tc_ok && cnn->mode > 0 && !ctx->slab && g.nb == 1 &&
+      !s->p_bc.data && mc->advection_method >= 0 && mc->advection_method <= 5) {
+    if (has_density && (check_scalar(ctx, &s->density, "density") || !same_spatial(&s->density, &s->flags)))
+      return fail(ctx, "Size mismatch");
+    return simulate_step_fused(ctx, s, mc, cnn, g);
+  }
   // 1-2. advect scalars then velocity (lib/simulate.lua:183-199).
   if (has_density && tfl_advect_scalar(ctx, mc->dt, &s->density, &s->U, &s->flags, mc->advection_method, 0,
                                        mc->maccormack_strength, nullptr))

@@ -332,4 +332,121 @@ __device__ inline bool line_trace(const float* __restrict__ fl, const Geo& g, V3
   return false;
 }
 
+// ---------------------------------------------------------------------------------------
+// Launch geometry shared by the per-cell kernels.
+// ---------------------------------------------------------------------------------------
+// (b, k, j, i) of this thread; returns false if outside the launch range.
+__device__ __forceinline__ bool thread_cell(const Geo& g, int& b, int& k, int& j, int& i) {
+  i = blockIdx.x * blockDim.x + threadIdx.x;
+  j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
+  const int nzr = g.zhi - g.zlo;
+  b = zz / nzr;
+  k = g.zlo + (zz - b * nzr);
+  return i < g.nx && j < g.ny && b < g.nb;
+}
+
+static inline void launch_dims(const Geo& g, dim3& grid, dim3& block) {
+  const int nzr = g.zhi - g.zlo;
+  if (g.nz == 1) block = dim3(32, 8, 1);
+  else block = dim3(32, 4, 2);
+  if (g.nx > 32 && g.nx % 64 == 0) { block.x = 64; block.y = (g.nz == 1) ? 4 : 2; }
+  grid = dim3((g.nx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
+              ((long long)g.nb * nzr + block.z - 1) / block.z);
+}
+
+
+// Which velocity components setWallBcsForward zeroes at (i, j, k)
+// (third_party/tfluids.cc:926-1002).
+__device__ __forceinline__ void wall_bc_zero_mask(const float* __restrict__ fl, const Geo& g, int k,
+                                                  int j, int i, bool z[3]) {
+  z[0] = z[1] = z[2] = false;
+  const int fc = flag_i(fl, g, k, j, i);
+  const bool cf = fc & kFluid, co = fc & kObstacle;
+  if (!cf && !co) return;
+  const int kg = k + g.zoff;
+  if (i > 0) {
+    const int f = flag_i(fl, g, k, j, i - 1);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[0] = true;
+  }
+  if (j > 0) {
+    const int f = flag_i(fl, g, k, j - 1, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[1] = true;
+  }
+  if (kg > 0) {
+    const int f = flag_i(fl, g, local_z(g, kg - 1), j, i);
+    if ((f & kObstacle) || (co && (f & kFluid))) z[2] = true;
+  }
+  if (cf) {
+    if ((i > 0 && (flag_i(fl, g, k, j, i - 1) & kStick)) ||
+        (i < g.nx - 1 && (flag_i(fl, g, k, j, i + 1) & kStick))) { z[1] = true; if (g.is3d) z[2] = true; }
+    if ((j > 0 && (flag_i(fl, g, k, j - 1, i) & kStick)) ||
+        (j < g.ny - 1 && (flag_i(fl, g, k, j + 1, i) & kStick))) { z[0] = true; if (g.is3d) z[2] = true; }
+    if (g.is3d && ((kg > 0 && (flag_i(fl, g, local_z(g, kg - 1), j, i) & kStick)) ||
+                   (kg < g.gnz - 1 && (flag_i(fl, g, local_z(g, kg + 1), j, i) & kStick)))) {
+      z[0] = true; z[1] = true;
+    }
+  }
+}
+
+
+// Vorticity-confinement force at one cell from the stored curl / |curl| fields
+// (third_party/tfluids.cc:1411-1439).
+__device__ __forceinline__ V3 conf_force(const float* __restrict__ cb, const float* __restrict__ cn,
+                                         const Geo& g, int k, int j, int i, float strength) {
+  if (on_border(g, k, j, i)) return V3{0.0f, 0.0f, 0.0f};
+  const long long c = cell(g, k, j, i);
+  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  V3 gr = {0.0f, 0.0f, 0.0f};
+  gr.x = 0.5f * (__ldg(cn + c + 1) - __ldg(cn + c - 1));
+  gr.y = 0.5f * (__ldg(cn + c + sy) - __ldg(cn + c - sy));
+  if (g.is3d) gr.z = 0.5f * (__ldg(cn + c + sz) - __ldg(cn + c - sz));
+  const float gn = norm3(gr);
+  if (gn > 1e-6f) { gr.x /= gn; gr.y /= gn; gr.z /= gn; } else { gr.x = gr.y = gr.z = 0.0f; }
+  const V3 w = {__ldg(cb + c), __ldg(cb + g.n + c), __ldg(cb + 2 * g.n + c)};
+  V3 f;
+  f.x = ((gr.y * w.z) - (gr.z * w.y)) * strength;
+  f.y = ((gr.z * w.x) - (gr.x * w.z)) * strength;
+  f.z = ((gr.x * w.y) - (gr.y * w.x)) * strength;
+  return f;
+}
+
+
+// nn.StandardDeviation + nn.Clamp on the accumulated sums (lib/modules/variance.lua:44-76).
+__device__ __forceinline__ float scale_from_sums(const double* __restrict__ sums, int b, long long n,
+                                                 float threshold) {
+  const float sum = (float)sums[2 * b], sumsq = (float)sums[2 * b + 1];
+  float out = sumsq * (float)n;
+  out = out + (-1.0f) * (sum * sum);
+  out = out / (float)((double)n * (double)(n - 1));
+  out = sqrtf(out);
+  return (out < threshold) ? threshold : out;
+}
+
+// Block-wide sum of (s, ss) -> two atomics per block.  All threads of the block must call.
+__device__ __forceinline__ void block_accumulate(double s, double ss, double* __restrict__ dst) {
+  __shared__ double sh[2][32];
+  const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  const int lane = tid & 31, w = tid >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    ss += __shfl_down_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) { sh[0][w] = s; sh[1][w] = ss; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+    s = lane < nw ? sh[0][lane] : 0.0;
+    ss = lane < nw ? sh[1][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_down_sync(0xffffffffu, s, o);
+      ss += __shfl_down_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      atomicAdd(dst, s);
+      atomicAdd(dst + 1, ss);
+    }
+  }
+}
+
 }  // namespace tfl

@@ -44,6 +44,21 @@ void launch_cnn_inputs_padded(const float* p_div, const float* U1, const float* 
 void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, const float* scale,
                        float* p_out, float* U_out, const Geo& g, cudaStream_t st);
 
+// ---- tfl_fused.cu (-fmad=false): fused point-wise stages of the convnet step ----
+void launch_post_advect(const float* tmp_s, const float* tmp_u, const float* flags, float* density, float* U,
+                        const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
+                        int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
+void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st);
+void launch_vort_bc_mask(float* U, const float* flags, const float* curl, const float* cnorm, int do_vort,
+                         float strength, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
+                         const Geo& g, cudaStream_t st);
+void launch_cnn_inputs_fused(const float* p_div, const float* U1, const float* flags, const double* sums,
+                             float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
+                             cudaStream_t st);
+void launch_cnn_finish_fused(const float* p_net, float* U, const float* flags, const float* scale, float* p_out,
+                             const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
+                             cudaStream_t st);
+
 // ---- tfl_cnn.cu ----
 // Generic direct convolution (fp32 FMA): in [b][cin][z][y][x] -> out [b][cout][z][y][x].
 // wdev: device weights re-laid out as [cin][tap][cout_pad], bias [cout].

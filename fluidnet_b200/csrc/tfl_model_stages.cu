@@ -9,65 +9,15 @@
 
 namespace tfl {
 
-__device__ __forceinline__ bool thread_cell2(const Geo& g, int& b, int& k, int& j, int& i) {
-  i = blockIdx.x * blockDim.x + threadIdx.x;
-  j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
-  const int nzr = g.zhi - g.zlo;
-  b = zz / nzr;
-  k = g.zlo + (zz - b * nzr);
-  return i < g.nx && j < g.ny && b < g.nb;
-}
-static void launch_dims2(const Geo& g, dim3& grid, dim3& block) {
-  const int nzr = g.zhi - g.zlo;
-  block = (g.nz == 1) ? dim3(32, 8, 1) : dim3(32, 4, 2);
-  grid = dim3((g.nx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
-              ((long long)g.nb * nzr + block.z - 1) / block.z);
-}
-
-// Which velocity components setWallBcsForward zeroes at (i, j, k)
-// (third_party/tfluids.cc:926-1002); duplicated from tfl_stencils.cu on purpose so each
-// translation unit stays self-contained.
-__device__ __forceinline__ void wall_zero(const float* __restrict__ fl, const Geo& g, int k, int j, int i,
-                                          bool z[3]) {
-  z[0] = z[1] = z[2] = false;
-  const int fc = flag_i(fl, g, k, j, i);
-  const bool cf = fc & kFluid, co = fc & kObstacle;
-  if (!cf && !co) return;
-  const int kg = k + g.zoff;
-  if (i > 0) {
-    const int f = flag_i(fl, g, k, j, i - 1);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[0] = true;
-  }
-  if (j > 0) {
-    const int f = flag_i(fl, g, k, j - 1, i);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[1] = true;
-  }
-  if (kg > 0) {
-    const int f = flag_i(fl, g, local_z(g, kg - 1), j, i);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[2] = true;
-  }
-  if (cf) {
-    if ((i > 0 && (flag_i(fl, g, k, j, i - 1) & kStick)) ||
-        (i < g.nx - 1 && (flag_i(fl, g, k, j, i + 1) & kStick))) { z[1] = true; if (g.is3d) z[2] = true; }
-    if ((j > 0 && (flag_i(fl, g, k, j - 1, i) & kStick)) ||
-        (j < g.ny - 1 && (flag_i(fl, g, k, j + 1, i) & kStick))) { z[0] = true; if (g.is3d) z[2] = true; }
-    if (g.is3d && ((kg > 0 && (flag_i(fl, g, local_z(g, kg - 1), j, i) & kStick)) ||
-                   (kg < g.gnz - 1 && (flag_i(fl, g, local_z(g, kg + 1), j, i) & kStick)))) {
-      z[0] = true; z[1] = true;
-    }
-  }
-}
-
 // U1 = U * wallmask; sums[b] += (sum U1, sum U1^2) over the launch range (double).
 __global__ void k_cnn_mask_stats(const float* __restrict__ U, const float* __restrict__ flags,
                                  float* __restrict__ U1, double* __restrict__ sums, Geo g) {
   int b, k, j, i;
-  const bool live = thread_cell2(g, b, k, j, i);
+  const bool live = thread_cell(g, b, k, j, i);
   double s = 0.0, ss = 0.0;
   if (live) {
     bool z[3];
-    wall_zero(flags + b * g.n, g, k, j, i, z);
+    wall_bc_zero_mask(flags + b * g.n, g, k, j, i, z);
     const long long c = (long long)b * g.nc * g.n + cell(g, k, j, i);
     for (int a = 0; a < g.nc; a++) {
       float u = U[c + a * g.n];
@@ -78,22 +28,13 @@ __global__ void k_cnn_mask_stats(const float* __restrict__ U, const float* __res
       ss += (double)sq;
     }
   }
-  // A block may straddle two batch entries only when nb > 1 and the z range is odd; keep
-  // it simple and correct: reduce per warp, then one atomic per warp and batch entry.
-  const unsigned lane = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
-  const int b0 = __shfl_sync(0xffffffffu, live ? b : -1, 0);
-  const bool uniform = __all_sync(0xffffffffu, (live ? b : -1) == b0 || !live);
-  if (uniform) {
-    int bb = live ? b : -1;
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_down_sync(0xffffffffu, s, o);
-      ss += __shfl_down_sync(0xffffffffu, ss, o);
-      bb = max(bb, __shfl_down_sync(0xffffffffu, bb, o));
-    }
-    if ((lane & 31) == 0 && bb >= 0) {
-      atomicAdd(sums + 2 * bb, s);
-      atomicAdd(sums + 2 * bb + 1, ss);
-    }
+  // One block never straddles two batch entries unless nb > 1 and the z range is odd; in that
+  // (rare) case fall back to per-thread atomics.
+  const int nzr = g.zhi - g.zlo;
+  const bool block_uniform = (g.nb == 1) || (nzr % (int)blockDim.z == 0);
+  if (block_uniform) {
+    const int zz0 = blockIdx.z * blockDim.z;
+    block_accumulate(s, ss, sums + 2 * (zz0 / nzr < g.nb ? zz0 / nzr : 0));
   } else if (live) {
     atomicAdd(sums + 2 * b, s);
     atomicAdd(sums + 2 * b + 1, ss);
@@ -105,12 +46,7 @@ __global__ void k_cnn_scale(const double* __restrict__ sums, float* __restrict__
                             long long n, float threshold) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const float sum = (float)sums[2 * b], sumsq = (float)sums[2 * b + 1];
-  float out = sumsq * (float)n;
-  out = out + (-1.0f) * (sum * sum);
-  out = out / (float)((double)n * (double)(n - 1));
-  out = sqrtf(out);
-  scale[b] = (out < threshold) ? threshold : out;      // also maps NaN -> NaN like nn.Clamp? (NaN < t is false)
+  scale[b] = scale_from_sums(sums, b, n, threshold);
 }
 
 // x0 = [pDiv / scale, div(U1) / scale, occupancy(flags)]
@@ -118,7 +54,7 @@ __global__ void k_cnn_inputs(const float* __restrict__ p_div, const float* __res
                              const float* __restrict__ flags, const float* __restrict__ scale,
                              float* __restrict__ x0, Geo g) {
   int b, k, j, i;
-  if (!thread_cell2(g, b, k, j, i)) return;
+  if (!thread_cell(g, b, k, j, i)) return;
   const long long c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
   const float* ub = U1 + (long long)b * g.nc * g.n;
@@ -140,7 +76,7 @@ __global__ void k_cnn_inputs_padded(const float* __restrict__ p_div, const float
                                     const float* __restrict__ flags, const float* __restrict__ scale,
                                     float4* __restrict__ x0, int px, int py, Geo g) {
   int b, k, j, i;
-  if (!thread_cell2(g, b, k, j, i)) return;
+  if (!thread_cell(g, b, k, j, i)) return;
   const long long c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
   const float* ub = U1 + (long long)b * g.nc * g.n;
@@ -161,7 +97,7 @@ __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __res
                              const float* __restrict__ flags, const float* __restrict__ scale,
                              float* __restrict__ p_out, float* __restrict__ U_out, Geo g) {
   int b, k, j, i;
-  if (!thread_cell2(g, b, k, j, i)) return;
+  if (!thread_cell(g, b, k, j, i)) return;
   const long long c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
   const float* fl = flags + b * g.n;
@@ -190,7 +126,7 @@ __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __res
     }
   }
   bool z[3];
-  wall_zero(fl, g, k, j, i, z);
+  wall_bc_zero_mask(fl, g, k, j, i, z);
   float* uo = U_out + (long long)b * g.nc * g.n + c;
   for (int a = 0; a < g.nc; a++) {
     float v = u[a] * sc;
@@ -203,7 +139,7 @@ __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __res
 #define TFL_LAUNCH3B(kernel, g, st, ...)           \
   do {                                             \
     dim3 grid_, block_;                            \
-    launch_dims2(g, grid_, block_);                \
+    launch_dims(g, grid_, block_);                \
     kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
   } while (0)
 

@@ -15,26 +15,6 @@
 
 namespace tfl {
 
-// (b, k, j, i) of this thread; returns false if outside the launch range.
-__device__ __forceinline__ bool thread_cell(const Geo& g, int& b, int& k, int& j, int& i) {
-  i = blockIdx.x * blockDim.x + threadIdx.x;
-  j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
-  const int nzr = g.zhi - g.zlo;
-  b = zz / nzr;
-  k = g.zlo + (zz - b * nzr);
-  return i < g.nx && j < g.ny && b < g.nb;
-}
-
-static void launch_dims(const Geo& g, dim3& grid, dim3& block) {
-  const int nzr = g.zhi - g.zlo;
-  if (g.nz == 1) block = dim3(32, 8, 1);
-  else block = dim3(32, 4, 2);
-  if (g.nx > 32 && g.nx % 64 == 0) { block.x = 64; block.y = (g.nz == 1) ? 4 : 2; }
-  grid = dim3((g.nx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
-              ((long long)g.nb * nzr + block.z - 1) / block.z);
-}
-
 // ---------------------------------------------------------------------------------------
 // emptyDomain / flagsToOccupancy
 // ---------------------------------------------------------------------------------------
@@ -62,37 +42,6 @@ __global__ void k_flags_to_occupancy(const float* __restrict__ flags, float* __r
 // ---------------------------------------------------------------------------------------
 // setWallBcsForward
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void wall_bc_zero_mask(const float* __restrict__ fl, const Geo& g, int k,
-                                                  int j, int i, bool z[3]) {
-  z[0] = z[1] = z[2] = false;
-  const int fc = flag_i(fl, g, k, j, i);
-  const bool cf = fc & kFluid, co = fc & kObstacle;
-  if (!cf && !co) return;
-  const int kg = k + g.zoff;
-  if (i > 0) {
-    const int f = flag_i(fl, g, k, j, i - 1);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[0] = true;
-  }
-  if (j > 0) {
-    const int f = flag_i(fl, g, k, j - 1, i);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[1] = true;
-  }
-  if (kg > 0) {
-    const int f = flag_i(fl, g, local_z(g, kg - 1), j, i);
-    if ((f & kObstacle) || (co && (f & kFluid))) z[2] = true;
-  }
-  if (cf) {
-    if ((i > 0 && (flag_i(fl, g, k, j, i - 1) & kStick)) ||
-        (i < g.nx - 1 && (flag_i(fl, g, k, j, i + 1) & kStick))) { z[1] = true; if (g.is3d) z[2] = true; }
-    if ((j > 0 && (flag_i(fl, g, k, j - 1, i) & kStick)) ||
-        (j < g.ny - 1 && (flag_i(fl, g, k, j + 1, i) & kStick))) { z[0] = true; if (g.is3d) z[2] = true; }
-    if (g.is3d && ((kg > 0 && (flag_i(fl, g, local_z(g, kg - 1), j, i) & kStick)) ||
-                   (kg < g.gnz - 1 && (flag_i(fl, g, local_z(g, kg + 1), j, i) & kStick)))) {
-      z[0] = true; z[1] = true;
-    }
-  }
-}
-
 __global__ void k_set_wall_bcs(float* __restrict__ U, const float* __restrict__ flags, Geo g,
                                int as_mask) {
   int b, k, j, i;
@@ -232,25 +181,6 @@ __global__ void k_vort_curl(const float* __restrict__ U, float* __restrict__ cur
   float* cb = curl + (long long)b * 3 * g.n;
   cb[c] = w.x; cb[g.n + c] = w.y; cb[2 * g.n + c] = w.z;
   cnorm[b * g.n + c] = nrm;
-}
-
-__device__ __forceinline__ V3 conf_force(const float* __restrict__ cb, const float* __restrict__ cn,
-                                         const Geo& g, int k, int j, int i, float strength) {
-  if (on_border(g, k, j, i)) return V3{0.0f, 0.0f, 0.0f};
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
-  V3 gr = {0.0f, 0.0f, 0.0f};
-  gr.x = 0.5f * (__ldg(cn + c + 1) - __ldg(cn + c - 1));
-  gr.y = 0.5f * (__ldg(cn + c + sy) - __ldg(cn + c - sy));
-  if (g.is3d) gr.z = 0.5f * (__ldg(cn + c + sz) - __ldg(cn + c - sz));
-  const float gn = norm3(gr);
-  if (gn > 1e-6f) { gr.x /= gn; gr.y /= gn; gr.z /= gn; } else { gr.x = gr.y = gr.z = 0.0f; }
-  const V3 w = {__ldg(cb + c), __ldg(cb + g.n + c), __ldg(cb + 2 * g.n + c)};
-  V3 f;
-  f.x = ((gr.y * w.z) - (gr.z * w.y)) * strength;
-  f.y = ((gr.z * w.x) - (gr.x * w.z)) * strength;
-  f.z = ((gr.x * w.y) - (gr.y * w.x)) * strength;
-  return f;
 }
 
 __global__ void k_vort_apply(float* __restrict__ U, const float* __restrict__ flags,
@@ -715,6 +645,12 @@ void launch_add_buoyancy(float* U, const float* flags, const float* rho, const f
 }
 void launch_add_gravity(float* U, const float* flags, const float f[3], const Geo& g, cudaStream_t st) {
   TFL_LAUNCH3(k_add_gravity, g, st, U, flags, f[0], f[1], f[2], g);
+}
+void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st) {
+  Geo g1 = g;
+  g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
+  g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
+  TFL_LAUNCH3(k_vort_curl, g1, st, U, curl, cnorm, g1);
 }
 int launch_vorticity(float* U, const float* flags, float strength, float* curl, float* cnorm, const Geo& g,
                      cudaStream_t st) {
