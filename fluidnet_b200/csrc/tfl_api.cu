@@ -701,7 +701,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   const bool has_density = s->density.data != nullptr;
   if (cnn_ensure_act(ctx, m, g)) return 1;
   if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4, cells * 4 * g.nc, cells * 4 * g.nc,
-                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb})))
+                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells})))
     return 1;
   Carver cv(ctx);
   float* fwd_s = cv.take<float>(cells);
@@ -713,15 +713,19 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   float* cnorm = cv.take<float>(cells);
   float* p_net = cv.take<float>(cells);
   float* scale = cv.take<float>(g.nb);
+  unsigned char* fl8 = cv.take<unsigned char>(cells);
   cudaStream_t st = ctx->stream;
+  // Byte copy of the flags for this step (every bit the kernels test is below 256).
+  launch_flags_to_u8(s->flags.data, fl8, (long long)cells, st);
+  ctx->launches += 1;
   if (has_density) {
-    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, s->flags.data, mc->advection_method, 0,
+    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, mc->advection_method, 0,
                                         mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, st);
     if (nl < 0) return fail(ctx, "advectScalar: bad method");
     ctx->launches += nl;
   }
   {
-    const int nl = launch_advect_vel(mc->dt, s->U.data, s->flags.data, mc->advection_method,
+    const int nl = launch_advect_vel(mc->dt, s->U.data, fl8, mc->advection_method,
                                      mc->maccormack_strength, tmp_u, fwd_u, g, g, st);
     if (nl < 0) return fail(ctx, "advectVel: bad method");
     ctx->launches += nl;
@@ -737,7 +741,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     const float scale_dt = mc->dt / get_dx(g);
     for (int a = 0; a < 3; a++) bs[a] = (-(mc->gravity[a] * k)) * scale_dt;
   }
-  launch_post_advect(has_density ? tmp_s : nullptr, tmp_u, s->flags.data, has_density ? s->density.data : nullptr,
+  launch_post_advect(has_density ? tmp_s : nullptr, tmp_u, fl8, has_density ? s->density.data : nullptr,
                      s->U.data, u_bc ? s->U_bc_inv_mask.data : nullptr, u_bc ? s->U_bc.data : nullptr,
                      d_bc ? s->density_bc_inv_mask.data : nullptr, d_bc ? s->density_bc.data : nullptr, do_buoy, bs,
                      g, st);
@@ -746,7 +750,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     const float k = (float)((-dx / 4.0) * mc->gravity_scale);
     const float scale_dt = mc->dt / get_dx(g);
     const float f[3] = {(mc->gravity[0] * k) * scale_dt, (mc->gravity[1] * k) * scale_dt, (mc->gravity[2] * k) * scale_dt};
-    launch_add_gravity(s->U.data, s->flags.data, f, g, st);
+    launch_add_gravity(s->U.data, fl8, f, g, st);
     ctx->launches += 1;
   }
   const int do_vort = mc->vorticity_confinement_amp > 0.0;
@@ -757,16 +761,16 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   }
   double* sums = ctx->dscratch + 64;
   TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
-  launch_vort_bc_mask(s->U.data, s->flags.data, curl, cnorm, do_vort, amp, u_bc ? s->U_bc_inv_mask.data : nullptr,
+  launch_vort_bc_mask(s->U.data, fl8, curl, cnorm, do_vort, amp, u_bc ? s->U_bc_inv_mask.data : nullptr,
                       u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
   const ConvTcGeo& tg = m->act_geo;
   const int split = m->mode == 2 ? 1 : 0;
-  launch_cnn_inputs_fused(s->p.data, s->U.data, s->flags.data, sums, mc->normalize_input_threshold, scale, m->act[0],
+  launch_cnn_inputs_fused(s->p.data, s->U.data, fl8, sums, mc->normalize_input_threshold, scale, m->act[0],
                           tg.px, tg.py, g, st);
   launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
   launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
   launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
-  launch_cnn_finish_fused(p_net, s->U.data, s->flags.data, scale, s->p.data, u_bc ? s->U_bc_inv_mask.data : nullptr,
+  launch_cnn_finish_fused(p_net, s->U.data, fl8, scale, s->p.data, u_bc ? s->U_bc_inv_mask.data : nullptr,
                           u_bc ? s->U_bc.data : nullptr, -1e6f, 1e6f, g, st);
   ctx->launches += 6;
   return check_launch(ctx, "simulate_step (fused)");

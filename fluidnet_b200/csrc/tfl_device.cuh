@@ -35,13 +35,30 @@ struct Geo {
 
 struct V3 { float x, y, z; };
 
+// Kernels are specialised on the dimensionality: copying the geometry and overwriting the two
+// fields with compile-time constants lets the compiler prune 2-D/3-D branches and unroll the
+// per-component loops.
+template <bool IS3D>
+__device__ __forceinline__ Geo static_geo(const Geo& gin) {
+  Geo g = gin;
+  g.is3d = IS3D ? 1 : 0;
+  g.nc = IS3D ? 3 : 2;
+  return g;
+}
+
 enum : int { kFluid = 1, kObstacle = 2, kEmpty = 4, kOutflow = 16, kStick = 128 };
 
-__device__ __forceinline__ long long cell(const Geo& g, int k, int j, int i) {
-  return ((long long)k * g.ny + j) * g.nx + i;
+// Offsets inside one (batch, channel) block fit 32 bits (n < 2^31, checked on the host).
+__device__ __forceinline__ int cell(const Geo& g, int k, int j, int i) {
+  return (k * g.ny + j) * g.nx + i;
 }
-__device__ __forceinline__ int flag_i(const float* __restrict__ fl, const Geo& g, int k, int j, int i) {
-  return (int)__ldg(fl + cell(g, k, j, i));
+// Flags come either as the API's float bit codes or as the byte copy the fused step makes
+// once per step (same low 8 bits: every bit the kernels test is below 256).
+__device__ __forceinline__ int flag_at(const float* __restrict__ fl, int o) { return (int)__ldg(fl + o); }
+__device__ __forceinline__ int flag_at(const unsigned char* __restrict__ fl, int o) { return (int)__ldg(fl + o); }
+template <typename FT>
+__device__ __forceinline__ int flag_i(const FT* __restrict__ fl, const Geo& g, int k, int j, int i) {
+  return flag_at(fl, cell(g, k, j, i));
 }
 // k is LOCAL here; the border is defined on the global grid.
 __device__ __forceinline__ bool on_border(const Geo& g, int k, int j, int i) {
@@ -101,7 +118,7 @@ __device__ __forceinline__ Lerp build_index(const Geo& g, V3 pos) {
 
 // Address of the (xi, yi, zi) corner in local storage; faults if the 2-plane footprint
 // leaves the slab.
-__device__ __forceinline__ long long corner(const Geo& g, const Lerp& q) {
+__device__ __forceinline__ int corner(const Geo& g, const Lerp& q) {
   int kl = q.zi - g.zoff;
   if (g.is3d) {
     if (kl < 0 || kl + 1 >= g.nz) { note_fault(g); kl = kl < 0 ? 0 : g.nz - 2; }
@@ -112,8 +129,8 @@ __device__ __forceinline__ long long corner(const Geo& g, const Lerp& q) {
 }
 
 __device__ __forceinline__ float lerp_at(const float* __restrict__ blk, const Geo& g,
-                                         const Lerp& q, long long o) {
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+                                         const Lerp& q, int o) {
+  const int sy = g.nx, sz = g.nx * g.ny;
   const float* a = blk + o;
   if (g.is3d) {
     const float lo = ((__ldg(a) * q.t0 + __ldg(a + sy) * q.t1) * q.s0 +
@@ -139,16 +156,18 @@ __device__ __forceinline__ FluidVal pair_fluid(FluidVal a, FluidVal b, float ta,
   else { r.v = a.v * ta + b.v * tb; r.ok = true; }
   return r;
 }
+template <typename FT>
 __device__ __forceinline__ FluidVal fluid_val(const float* __restrict__ blk,
-                                              const float* __restrict__ fl, long long o) {
-  return FluidVal{__ldg(blk + o), (((int)__ldg(fl + o)) & kFluid) != 0};
+                                              const FT* __restrict__ fl, int o) {
+  return FluidVal{__ldg(blk + o), (flag_at(fl, o) & kFluid) != 0};
 }
+template <typename FT>
 __device__ __forceinline__ float lerp_block_fluid(const float* __restrict__ blk,
-                                                  const float* __restrict__ fl, const Geo& g,
+                                                  const FT* __restrict__ fl, const Geo& g,
                                                   V3 pos) {
   const Lerp q = build_index(g, pos);
-  const long long o = corner(g, q);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int o = corner(g, q);
+  const int sy = g.nx, sz = g.nx * g.ny;
   FluidVal all;
   const FluidVal ab = pair_fluid(fluid_val(blk, fl, o), fluid_val(blk, fl, o + sy), q.t0, q.t1);
   const FluidVal cd = pair_fluid(fluid_val(blk, fl, o + 1), fluid_val(blk, fl, o + sy + 1), q.t0, q.t1);
@@ -168,8 +187,8 @@ __device__ __forceinline__ float lerp_block_fluid(const float* __restrict__ blk,
 // MAC-grid samples at cell (i, j, k) (k local).  Ub points at channel 0 of one batch.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ V3 mac_centered(const float* __restrict__ Ub, const Geo& g, int k, int j, int i) {
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int c = cell(g, k, j, i);
+  const int sy = g.nx, sz = g.nx * g.ny;
   V3 r;
   r.x = 0.5f * (__ldg(Ub + c) + __ldg(Ub + c + 1));
   r.y = 0.5f * (__ldg(Ub + g.n + c) + __ldg(Ub + g.n + c + sy));
@@ -177,8 +196,8 @@ __device__ __forceinline__ V3 mac_centered(const float* __restrict__ Ub, const G
   return r;
 }
 __device__ __forceinline__ V3 mac_at_x(const float* __restrict__ Ub, const Geo& g, int k, int j, int i) {
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int c = cell(g, k, j, i);
+  const int sy = g.nx, sz = g.nx * g.ny;
   const float* uy = Ub + g.n;
   const float* uz = Ub + 2 * g.n;
   V3 r;
@@ -189,8 +208,8 @@ __device__ __forceinline__ V3 mac_at_x(const float* __restrict__ Ub, const Geo& 
   return r;
 }
 __device__ __forceinline__ V3 mac_at_y(const float* __restrict__ Ub, const Geo& g, int k, int j, int i) {
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int c = cell(g, k, j, i);
+  const int sy = g.nx, sz = g.nx * g.ny;
   const float* uy = Ub + g.n;
   const float* uz = Ub + 2 * g.n;
   V3 r;
@@ -201,8 +220,8 @@ __device__ __forceinline__ V3 mac_at_y(const float* __restrict__ Ub, const Geo& 
   return r;
 }
 __device__ __forceinline__ V3 mac_at_z(const float* __restrict__ Ub, const Geo& g, int k, int j, int i) {
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int c = cell(g, k, j, i);
+  const int sy = g.nx, sz = g.nx * g.ny;
   const float* uy = Ub + g.n;
   const float* uz = Ub + 2 * g.n;
   V3 r;
@@ -222,7 +241,8 @@ __device__ __forceinline__ bool out_of_domain(const Geo& g, V3 p) {
   return p.x <= 0.0f || p.x >= (float)g.nx || p.y <= 0.0f || p.y >= (float)g.ny ||
          p.z <= 0.0f || p.z >= (float)g.gnz;
 }
-__device__ __forceinline__ bool blocked_at(const float* __restrict__ fl, const Geo& g, V3 p) {
+template <typename FT>
+__device__ __forceinline__ bool blocked_at(const FT* __restrict__ fl, const Geo& g, V3 p) {
   const int k = local_z(g, (int)p.z);
   return (flag_i(fl, g, k, (int)p.y, (int)p.x) & kFluid) == 0;
 }
@@ -287,7 +307,8 @@ __device__ inline bool ray_border(const Geo& g, V3 pos, V3 next, V3* ip) {
 }
 
 // Returns true if the trace was cut short (geometry or domain border).
-__device__ inline bool line_trace(const float* __restrict__ fl, const Geo& g, V3 pos, V3 delta,
+template <typename FT>
+__device__ inline bool line_trace(const FT* __restrict__ fl, const Geo& g, V3 pos, V3 delta,
                                   V3* out) {
   *out = pos;
   const float length = norm3(delta);
@@ -358,7 +379,8 @@ static inline void launch_dims(const Geo& g, dim3& grid, dim3& block) {
 
 // Which velocity components setWallBcsForward zeroes at (i, j, k)
 // (third_party/tfluids.cc:926-1002).
-__device__ __forceinline__ void wall_bc_zero_mask(const float* __restrict__ fl, const Geo& g, int k,
+template <typename FT>
+__device__ __forceinline__ void wall_bc_zero_mask(const FT* __restrict__ fl, const Geo& g, int k,
                                                   int j, int i, bool z[3]) {
   z[0] = z[1] = z[2] = false;
   const int fc = flag_i(fl, g, k, j, i);
@@ -395,8 +417,8 @@ __device__ __forceinline__ void wall_bc_zero_mask(const float* __restrict__ fl, 
 __device__ __forceinline__ V3 conf_force(const float* __restrict__ cb, const float* __restrict__ cn,
                                          const Geo& g, int k, int j, int i, float strength) {
   if (on_border(g, k, j, i)) return V3{0.0f, 0.0f, 0.0f};
-  const long long c = cell(g, k, j, i);
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int c = cell(g, k, j, i);
+  const int sy = g.nx, sz = g.nx * g.ny;
   V3 gr = {0.0f, 0.0f, 0.0f};
   gr.x = 0.5f * (__ldg(cn + c + 1) - __ldg(cn + c - 1));
   gr.y = 0.5f * (__ldg(cn + c + sy) - __ldg(cn + c - sy));

@@ -34,13 +34,15 @@ __device__ __forceinline__ float bc_apply(float x, const float* __restrict__ inv
 }
 
 // density = BC(tmp_s); U = BC(tmp_U) (+ buoyancy with the NEW density).
+template <bool IS3D, typename FT>
 __global__ void k_post_advect(const float* __restrict__ tmp_s, const float* __restrict__ tmp_u,
-                              const float* __restrict__ flags, float* __restrict__ density,
+                              const FT* __restrict__ flags, float* __restrict__ density,
                               float* __restrict__ U, BcPtrs bc, int do_buoy, float sx, float sy_, float sz_,
-                              Geo g) {
+                              Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const long long sb = b * g.n, ub = (long long)b * g.nc * g.n;
   float rc = 0.0f;
   if (density) {
@@ -50,9 +52,9 @@ __global__ void k_post_advect(const float* __restrict__ tmp_s, const float* __re
   float u[3];
   for (int a = 0; a < g.nc; a++) u[a] = bc_apply(__ldg(tmp_u + ub + a * g.n + c), bc.u_inv, bc.u_bc, ub + a * g.n + c);
   if (do_buoy && density && !on_border(g, k, j, i)) {
-    const float* fl = flags + sb;
+    const FT* fl = flags + sb;
     if (flag_i(fl, g, k, j, i) & kFluid) {
-      const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+      const int st[3] = {1, g.nx, g.nx * g.ny};
       const float str[3] = {sx, sy_, sz_};
       int fn[3];
       fn[0] = flag_i(fl, g, k, j, i - 1);
@@ -71,17 +73,19 @@ __global__ void k_post_advect(const float* __restrict__ tmp_s, const float* __re
 
 // U += confinement force; U = BC(U); then (mask_mode 1) U *= wall mask and accumulate the
 // sums for the input scale.
-__global__ void k_vort_bc_mask(float* __restrict__ U, const float* __restrict__ flags,
+template <bool IS3D, typename FT>
+__global__ void k_vort_bc_mask(float* __restrict__ U, const FT* __restrict__ flags,
                                const float* __restrict__ curl, const float* __restrict__ cnorm,
                                int do_vort, float strength, BcPtrs bc, int mask_mode,
-                               double* __restrict__ sums, Geo g) {
+                               double* __restrict__ sums, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   const bool live = thread_cell(g, b, k, j, i);
   double s = 0.0, ss = 0.0;
   if (live) {
-    const long long c = cell(g, k, j, i);
+    const int c = cell(g, k, j, i);
     const long long ub = (long long)b * g.nc * g.n;
-    const float* fl = flags + b * g.n;
+    const FT* fl = flags + b * g.n;
     float u[3];
     for (int a = 0; a < g.nc; a++) u[a] = U[ub + a * g.n + c];
     if (do_vort && !on_border(g, k, j, i)) {
@@ -122,13 +126,15 @@ __global__ void k_vort_bc_mask(float* __restrict__ U, const float* __restrict__ 
 
 // First channels-last plane of the conv input: (pDiv/s, div(U1)/s, occupancy, 0); U1 is the
 // already masked velocity left in U by k_vort_bc_mask.
+template <bool IS3D, typename FT>
 __global__ void k_cnn_inputs_fused(const float* __restrict__ p_div, const float* __restrict__ U1,
-                                   const float* __restrict__ flags, const double* __restrict__ sums,
+                                   const FT* __restrict__ flags, const double* __restrict__ sums,
                                    float threshold, float* __restrict__ scale_out, float4* __restrict__ x0,
-                                   int px, int py, Geo g) {
+                                   int px, int py, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float sc = scale_from_sums(sums, b, (long long)g.nc * g.n, threshold);
   if (c == 0) scale_out[b] = sc;
   const float* ub = U1 + (long long)b * g.nc * g.n;
@@ -145,21 +151,23 @@ __global__ void k_cnn_inputs_fused(const float* __restrict__ p_div, const float*
 }
 
 // U = clamp(BC(setWallBcs(velocityUpdate(U1 / s, p_net) * s)));  p = p_net * s.  In place on U.
+template <bool IS3D, typename FT>
 __global__ void k_cnn_finish_fused(const float* __restrict__ p_net, float* __restrict__ U,
-                                   const float* __restrict__ flags, const float* __restrict__ scale,
-                                   float* __restrict__ p_out, BcPtrs bc, float lo, float hi, Geo g) {
+                                   const FT* __restrict__ flags, const float* __restrict__ scale,
+                                   float* __restrict__ p_out, BcPtrs bc, float lo, float hi, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   const float* pb = p_net + b * g.n;
   const long long ub = (long long)b * g.nc * g.n;
   const float pc = __ldg(pb + c);
   float u[3];
   for (int a = 0; a < g.nc; a++) u[a] = U[ub + a * g.n + c] / sc;
   if (!on_border(g, k, j, i)) {
-    const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+    const int st[3] = {1, g.nx, g.nx * g.ny};
     const int fc = flag_i(fl, g, k, j, i);
     int fn[3];
     fn[0] = flag_i(fl, g, k, j, i - 1);
@@ -189,31 +197,32 @@ __global__ void k_cnn_finish_fused(const float* __restrict__ p_net, float* __res
   p_out[b * g.n + c] = pc * sc;
 }
 
-#define TFL_LAUNCH3F(kernel, g, st, ...)           \
-  do {                                             \
-    dim3 grid_, block_;                            \
-    launch_dims(g, grid_, block_);                 \
-    kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
+#define TFL_LAUNCH3F(kernel, g, st, ...)                                                \
+  do {                                                                                  \
+    dim3 grid_, block_;                                                                 \
+    launch_dims(g, grid_, block_);                                                      \
+    if ((g).is3d) kernel<true, unsigned char><<<grid_, block_, 0, st>>>(__VA_ARGS__);   \
+    else kernel<false, unsigned char><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
   } while (0)
 
-void launch_post_advect(const float* tmp_s, const float* tmp_u, const float* flags, float* density, float* U,
+void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, d_inv, d_bc};
   TFL_LAUNCH3F(k_post_advect, g, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
 }
-void launch_vort_bc_mask(float* U, const float* flags, const float* curl, const float* cnorm, int do_vort,
+void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* curl, const float* cnorm, int do_vort,
                          float strength, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
   TFL_LAUNCH3F(k_vort_bc_mask, g, st, U, flags, curl, cnorm, do_vort, strength, bc, mask_mode, sums, g);
 }
-void launch_cnn_inputs_fused(const float* p_div, const float* U1, const float* flags, const double* sums,
+void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
                              cudaStream_t st) {
   TFL_LAUNCH3F(k_cnn_inputs_fused, g, st, p_div, U1, flags, sums, threshold, scale_out, (float4*)x0, px, py, g);
 }
-void launch_cnn_finish_fused(const float* p_net, float* U, const float* flags, const float* scale, float* p_out,
+void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* flags, const float* scale, float* p_out,
                              const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
                              cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};

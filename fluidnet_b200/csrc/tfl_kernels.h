@@ -11,24 +11,34 @@ namespace tfl {
 void launch_empty_domain(float* flags, const Geo& g, int bnd, cudaStream_t st);
 void launch_flags_to_occupancy(const float* flags, float* occ, long long n, unsigned long long* bad,
                                cudaStream_t st);
-void launch_set_wall_bcs(float* U, const float* flags, const Geo& g, int as_mask, cudaStream_t st);
-void launch_divergence(const float* U, const float* flags, float* div, const Geo& g, cudaStream_t st);
-void launch_velocity_update(float* U, const float* flags, const float* p, const Geo& g, cudaStream_t st);
-void launch_add_buoyancy(float* U, const float* flags, const float* rho, const float s[3], const Geo& g,
+template <typename FT>
+void launch_set_wall_bcs(float* U, const FT* flags, const Geo& g, int as_mask, cudaStream_t st);
+template <typename FT>
+void launch_divergence(const float* U, const FT* flags, float* div, const Geo& g, cudaStream_t st);
+template <typename FT>
+void launch_velocity_update(float* U, const FT* flags, const float* p, const Geo& g, cudaStream_t st);
+template <typename FT>
+void launch_add_buoyancy(float* U, const FT* flags, const float* rho, const float s[3], const Geo& g,
                          cudaStream_t st);
-void launch_add_gravity(float* U, const float* flags, const float f[3], const Geo& g, cudaStream_t st);
-int launch_vorticity(float* U, const float* flags, float strength, float* curl, float* cnorm, const Geo& g,
+template <typename FT>
+void launch_add_gravity(float* U, const FT* flags, const float f[3], const Geo& g, cudaStream_t st);
+template <typename FT>
+int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, const Geo& g,
                      cudaStream_t st);
 // g: range of the result; g_fwd: (wider, in slab mode) range of the forward pass.
-int launch_advect_scalar(float dt, const float* s, const float* U, const float* flags, int method,
+template <typename FT>
+int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, int method,
                          int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
                          const Geo& g_fwd, cudaStream_t st);
-int launch_advect_vel(float dt, const float* U, const float* flags, int method, float strength, float* dst,
+template <typename FT>
+int launch_advect_vel(float dt, const float* U, const FT* flags, int method, float strength, float* dst,
                       float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st);
-void launch_jacobi_mask(const float* flags, unsigned char* mask, const Geo& g, cudaStream_t st);
+template <typename FT>
+void launch_jacobi_mask(const FT* flags, unsigned char* mask, const Geo& g, cudaStream_t st);
 void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
                         const Geo& g, cudaStream_t st);
 void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st);
+void launch_flags_to_u8(const float* f, unsigned char* o, long long n, cudaStream_t st);
 void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, cudaStream_t st);
 void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st);
 
@@ -45,17 +55,17 @@ void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, 
                        float* p_out, float* U_out, const Geo& g, cudaStream_t st);
 
 // ---- tfl_fused.cu (-fmad=false): fused point-wise stages of the convnet step ----
-void launch_post_advect(const float* tmp_s, const float* tmp_u, const float* flags, float* density, float* U,
+void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
 void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st);
-void launch_vort_bc_mask(float* U, const float* flags, const float* curl, const float* cnorm, int do_vort,
+void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* curl, const float* cnorm, int do_vort,
                          float strength, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st);
-void launch_cnn_inputs_fused(const float* p_div, const float* U1, const float* flags, const double* sums,
+void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
                              cudaStream_t st);
-void launch_cnn_finish_fused(const float* p_net, float* U, const float* flags, const float* scale, float* p_out,
+void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* flags, const float* scale, float* p_out,
                              const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
                              cudaStream_t st);
 

@@ -10,8 +10,10 @@
 namespace tfl {
 
 // U1 = U * wallmask; sums[b] += (sum U1, sum U1^2) over the launch range (double).
-__global__ void k_cnn_mask_stats(const float* __restrict__ U, const float* __restrict__ flags,
-                                 float* __restrict__ U1, double* __restrict__ sums, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_cnn_mask_stats(const float* __restrict__ U, const FT* __restrict__ flags,
+                                 float* __restrict__ U1, double* __restrict__ sums, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   const bool live = thread_cell(g, b, k, j, i);
   double s = 0.0, ss = 0.0;
@@ -50,12 +52,14 @@ __global__ void k_cnn_scale(const double* __restrict__ sums, float* __restrict__
 }
 
 // x0 = [pDiv / scale, div(U1) / scale, occupancy(flags)]
+template <bool IS3D, typename FT>
 __global__ void k_cnn_inputs(const float* __restrict__ p_div, const float* __restrict__ U1,
-                             const float* __restrict__ flags, const float* __restrict__ scale,
-                             float* __restrict__ x0, Geo g) {
+                             const FT* __restrict__ flags, const float* __restrict__ scale,
+                             float* __restrict__ x0, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
   const float* ub = U1 + (long long)b * g.nc * g.n;
   const int f = flag_i(flags + b * g.n, g, k, j, i);
@@ -72,12 +76,14 @@ __global__ void k_cnn_inputs(const float* __restrict__ p_div, const float* __res
 
 // Same three input channels written as the first channels-last float4 plane of the padded
 // activation layout the tensor-core convolution reads (tfl_cnn_tc.cu): (pDiv/s, div/s, occ, 0).
+template <bool IS3D, typename FT>
 __global__ void k_cnn_inputs_padded(const float* __restrict__ p_div, const float* __restrict__ U1,
-                                    const float* __restrict__ flags, const float* __restrict__ scale,
-                                    float4* __restrict__ x0, int px, int py, Geo g) {
+                                    const FT* __restrict__ flags, const float* __restrict__ scale,
+                                    float4* __restrict__ x0, int px, int py, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
   const float* ub = U1 + (long long)b * g.nc * g.n;
   const int f = flag_i(flags + b * g.n, g, k, j, i);
@@ -93,21 +99,23 @@ __global__ void k_cnn_inputs_padded(const float* __restrict__ p_div, const float
 }
 
 // U = setWallBcs(velocityUpdate(U1 / scale, p_net) * scale);  p = p_net * scale.
+template <bool IS3D, typename FT>
 __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __restrict__ U1,
-                             const float* __restrict__ flags, const float* __restrict__ scale,
-                             float* __restrict__ p_out, float* __restrict__ U_out, Geo g) {
+                             const FT* __restrict__ flags, const float* __restrict__ scale,
+                             float* __restrict__ p_out, float* __restrict__ U_out, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float sc = __ldg(scale + b);
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   const float* pb = p_net + b * g.n;
   const float* ub = U1 + (long long)b * g.nc * g.n;
   const float pc = __ldg(pb + c);
   float u[3];
   for (int a = 0; a < g.nc; a++) u[a] = __ldg(ub + a * g.n + c) / sc;
   if (!on_border(g, k, j, i)) {
-    const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+    const int st[3] = {1, g.nx, g.nx * g.ny};
     const int fc = flag_i(fl, g, k, j, i);
     int fn[3];
     fn[0] = flag_i(fl, g, k, j, i - 1);
@@ -136,11 +144,12 @@ __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __res
   p_out[b * g.n + c] = pc * sc;
 }
 
-#define TFL_LAUNCH3B(kernel, g, st, ...)           \
-  do {                                             \
-    dim3 grid_, block_;                            \
-    launch_dims(g, grid_, block_);                \
-    kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
+#define TFL_LAUNCH3B(kernel, g, st, ...)                                        \
+  do {                                                                          \
+    dim3 grid_, block_;                                                         \
+    launch_dims(g, grid_, block_);                                              \
+    if ((g).is3d) kernel<true, float><<<grid_, block_, 0, st>>>(__VA_ARGS__);   \
+    else kernel<false, float><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
   } while (0)
 
 void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, const Geo& g,

@@ -18,7 +18,9 @@ namespace tfl {
 // ---------------------------------------------------------------------------------------
 // emptyDomain / flagsToOccupancy
 // ---------------------------------------------------------------------------------------
-__global__ void k_empty_domain(float* __restrict__ flags, Geo g, int bnd) {
+template <bool IS3D, typename FT>
+__global__ void k_empty_domain(float* __restrict__ flags, Geo gin, int bnd) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const int kg = k + g.zoff;
@@ -42,8 +44,10 @@ __global__ void k_flags_to_occupancy(const float* __restrict__ flags, float* __r
 // ---------------------------------------------------------------------------------------
 // setWallBcsForward
 // ---------------------------------------------------------------------------------------
-__global__ void k_set_wall_bcs(float* __restrict__ U, const float* __restrict__ flags, Geo g,
+template <bool IS3D, typename FT>
+__global__ void k_set_wall_bcs(float* __restrict__ U, const FT* __restrict__ flags, Geo gin,
                                int as_mask) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   bool z[3];
@@ -56,11 +60,13 @@ __global__ void k_set_wall_bcs(float* __restrict__ U, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // velocityDivergenceForward  (returns u(i)-u(i+1)+..., i.e. minus the divergence)
 // ---------------------------------------------------------------------------------------
-__global__ void k_divergence(const float* __restrict__ U, const float* __restrict__ flags,
-                             float* __restrict__ div, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_divergence(const float* __restrict__ U, const FT* __restrict__ flags,
+                             float* __restrict__ div, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float* ub = U + (long long)b * g.nc * g.n;
   float r = 0.0f;
   if (!on_border(g, k, j, i) && (flag_i(flags + b * g.n, g, k, j, i) & kFluid)) {
@@ -73,16 +79,18 @@ __global__ void k_divergence(const float* __restrict__ U, const float* __restric
 // ---------------------------------------------------------------------------------------
 // velocityUpdateForward
 // ---------------------------------------------------------------------------------------
-__global__ void k_velocity_update(float* __restrict__ U, const float* __restrict__ flags,
-                                  const float* __restrict__ p, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_velocity_update(float* __restrict__ U, const FT* __restrict__ flags,
+                                  const float* __restrict__ p, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   if (on_border(g, k, j, i)) return;
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   const float* pb = p + b * g.n;
   float* ub = U + (long long)b * g.nc * g.n;
-  const long long c = cell(g, k, j, i);
-  const long long st[3] = {1, g.nx, (long long)g.nx * g.ny};
+  const int c = cell(g, k, j, i);
+  const int st[3] = {1, g.nx, g.nx * g.ny};
   const int fc = flag_i(fl, g, k, j, i);
   int fn[3];
   fn[0] = flag_i(fl, g, k, j, i - 1);
@@ -109,16 +117,18 @@ __global__ void k_velocity_update(float* __restrict__ U, const float* __restrict
 // ---------------------------------------------------------------------------------------
 // addBuoyancy / addGravity
 // ---------------------------------------------------------------------------------------
-__global__ void k_add_buoyancy(float* __restrict__ U, const float* __restrict__ flags,
-                               const float* __restrict__ rho, float sx, float sy_, float sz_, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_add_buoyancy(float* __restrict__ U, const FT* __restrict__ flags,
+                               const float* __restrict__ rho, float sx, float sy_, float sz_, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   if (on_border(g, k, j, i)) return;
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   if (!(flag_i(fl, g, k, j, i) & kFluid)) return;
   const float* rb = rho + b * g.n;
   float* ub = U + (long long)b * g.nc * g.n;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float rc = __ldg(rb + c);
   if (flag_i(fl, g, k, j, i - 1) & kFluid) ub[c] += (0.5f * sx * (rc + __ldg(rb + c - 1)));
   if (flag_i(fl, g, k, j - 1, i) & kFluid) ub[g.n + c] += (0.5f * sy_ * (rc + __ldg(rb + c - g.nx)));
@@ -126,17 +136,19 @@ __global__ void k_add_buoyancy(float* __restrict__ U, const float* __restrict__ 
     ub[2 * g.n + c] += (0.5f * sz_ * (rc + __ldg(rb + c - (long long)g.nx * g.ny)));
 }
 
-__global__ void k_add_gravity(float* __restrict__ U, const float* __restrict__ flags, float fx,
-                              float fy, float fz, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_add_gravity(float* __restrict__ U, const FT* __restrict__ flags, float fx,
+                              float fy, float fz, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   if (on_border(g, k, j, i)) return;
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   const int fc = flag_i(fl, g, k, j, i);
   const bool cf = fc & kFluid, ce = fc & kEmpty;
   if (!cf && !ce) return;
   float* ub = U + (long long)b * g.nc * g.n;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   int f = flag_i(fl, g, k, j, i - 1);
   if ((f & kFluid) || (cf && (f & kEmpty))) ub[c] += fx;
   f = flag_i(fl, g, k, j - 1, i);
@@ -159,12 +171,14 @@ __device__ __forceinline__ V3 centered_or_zero(const float* __restrict__ Ub, con
   return mac_centered(Ub, g, k, j, i);
 }
 
+template <bool IS3D, typename FT>
 __global__ void k_vort_curl(const float* __restrict__ U, float* __restrict__ curl,
-                            float* __restrict__ cnorm, Geo g) {
+                            float* __restrict__ cnorm, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const float* ub = U + (long long)b * g.nc * g.n;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   V3 w = {0.0f, 0.0f, 0.0f};
   float nrm = 0.0f;
   if (!on_border(g, k, j, i)) {
@@ -183,20 +197,22 @@ __global__ void k_vort_curl(const float* __restrict__ U, float* __restrict__ cur
   cnorm[b * g.n + c] = nrm;
 }
 
-__global__ void k_vort_apply(float* __restrict__ U, const float* __restrict__ flags,
+template <bool IS3D, typename FT>
+__global__ void k_vort_apply(float* __restrict__ U, const FT* __restrict__ flags,
                              const float* __restrict__ curl, const float* __restrict__ cnorm,
-                             float strength, Geo g) {
+                             float strength, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   if (on_border(g, k, j, i)) return;
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   const int fc = flag_i(fl, g, k, j, i);
   const bool cf = fc & kFluid, ce = fc & kEmpty;
   if (!cf && !ce) return;
   const float* cb = curl + (long long)b * 3 * g.n;
   const float* cn = cnorm + b * g.n;
   float* ub = U + (long long)b * g.nc * g.n;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const V3 f0 = conf_force(cb, cn, g, k, j, i, strength);
   int f = flag_i(fl, g, k, j, i - 1);
   if ((f & kFluid) || (cf && (f & kEmpty)))
@@ -214,7 +230,8 @@ __global__ void k_vort_apply(float* __restrict__ U, const float* __restrict__ fl
 // ---------------------------------------------------------------------------------------
 // advectScalar
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float sample_scalar(const float* __restrict__ src, const float* __restrict__ fl,
+template <typename FT>
+__device__ __forceinline__ float sample_scalar(const float* __restrict__ src, const FT* __restrict__ fl,
                                                const Geo& g, V3 pos, bool outside) {
   return outside ? lerp_block(src, g, pos) : lerp_block_fluid(src, fl, g, pos);
 }
@@ -230,8 +247,8 @@ __device__ __forceinline__ V3 sample_vel(const float* __restrict__ ub, const Geo
 
 // One semi-Lagrangian pass for an interior cell.  `pos_out` receives the trace end
 // point ("SavePos" variants) when non-null.
-template <int METHOD>
-__device__ __forceinline__ float advect_scalar_cell(const float* __restrict__ fl, const float* __restrict__ ub,
+template <int METHOD, typename FT>
+__device__ __forceinline__ float advect_scalar_cell(const FT* __restrict__ fl, const float* __restrict__ ub,
                                                     const float* __restrict__ src, const Geo& g, float dt,
                                                     int k, int j, int i, bool outside, V3* pos_out) {
   const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
@@ -272,13 +289,14 @@ __device__ __forceinline__ float advect_scalar_cell(const float* __restrict__ fl
   return sample_scalar(src, fl, g, back, outside);
 }
 
-template <int METHOD>
+template <bool IS3D, typename FT, int METHOD>
 __global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* __restrict__ U,
-                                      const float* __restrict__ flags, float* __restrict__ out,
-                                      float* __restrict__ pos_out, float dt, int outside, Geo g) {
+                                      const FT* __restrict__ flags, float* __restrict__ out,
+                                      float* __restrict__ pos_out, float dt, int outside, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   float v = 0.0f;
   V3 pos = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
   if (!on_border(g, k, j, i)) {
@@ -296,14 +314,16 @@ __global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* 
 // MacCormack (ours): backward trace on the forward field + correction + clamp to the
 // fluid neighbourhood of the forward trace position, fused
 // (third_party/tfluids.cc:521-583, 222-234, 331-413).
+template <bool IS3D, typename FT>
 __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const float* __restrict__ fwd,
                                            const float* __restrict__ fwd_pos, const float* __restrict__ U,
-                                           const float* __restrict__ flags, float* __restrict__ dst,
-                                           float dt, float strength, int outside, Geo g) {
+                                           const FT* __restrict__ flags, float* __restrict__ dst,
+                                           float dt, float strength, int outside, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
-  const float* fl = flags + b * g.n;
+  const int c = cell(g, k, j, i);
+  const FT* fl = flags + b * g.n;
   const float* sb = s + b * g.n;
   const float* fb = fwd + b * g.n;
   const float fw = __ldg(fb + c);
@@ -346,13 +366,15 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
 }
 
 // MacCormack (Manta): third_party/tfluids.cc:249-325.
+template <bool IS3D, typename FT>
 __global__ void k_advect_scalar_pass2_manta(const float* __restrict__ s, const float* __restrict__ fwd,
-                                            const float* __restrict__ U, const float* __restrict__ flags,
-                                            float* __restrict__ dst, float dt, float strength, Geo g) {
+                                            const float* __restrict__ U, const FT* __restrict__ flags,
+                                            float* __restrict__ dst, float dt, float strength, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
-  const float* fl = flags + b * g.n;
+  const int c = cell(g, k, j, i);
+  const FT* fl = flags + b * g.n;
   const float* sb = s + b * g.n;
   const float* fb = fwd + b * g.n;
   const float* ub = U + (long long)b * g.nc * g.n;
@@ -403,13 +425,13 @@ __global__ void k_advect_scalar_pass2_manta(const float* __restrict__ s, const f
 // ---------------------------------------------------------------------------------------
 // advectVel
 // ---------------------------------------------------------------------------------------
-template <bool OURS>
-__device__ __forceinline__ V3 advect_mac_cell(const float* __restrict__ fl, const float* __restrict__ ub,
+template <bool OURS, typename FT>
+__device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const float* __restrict__ ub,
                                               const float* __restrict__ src, const Geo& g, float dt, int k,
                                               int j, int i) {
   V3 r;
   if (OURS && !(flag_i(fl, g, k, j, i) & kFluid)) {
-    const long long c = cell(g, k, j, i);
+    const int c = cell(g, k, j, i);
     r.x = __ldg(src + c); r.y = __ldg(src + g.n + c); r.z = g.is3d ? __ldg(src + 2 * g.n + c) : 0.0f;
     return r;
   }
@@ -444,12 +466,13 @@ __device__ __forceinline__ V3 advect_mac_cell(const float* __restrict__ fl, cons
   return r;
 }
 
-template <bool OURS>
-__global__ void k_advect_vel_pass1(const float* __restrict__ U, const float* __restrict__ flags,
-                                   float* __restrict__ out, float dt, Geo g) {
+template <bool IS3D, typename FT, bool OURS>
+__global__ void k_advect_vel_pass1(const float* __restrict__ U, const FT* __restrict__ flags,
+                                   float* __restrict__ out, float dt, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
+  const int c = cell(g, k, j, i);
   const float* ub = U + (long long)b * g.nc * g.n;
   V3 v = {0.0f, 0.0f, 0.0f};
   if (!on_border(g, k, j, i)) v = advect_mac_cell<OURS>(flags + b * g.n, ub, ub, g, dt, k, j, i);
@@ -483,14 +506,15 @@ __device__ __forceinline__ float clamp_component_mac(const float* __restrict__ o
 
 // Backward pass on the forward field + MacCormackCorrectMAC + MacCormackClampMAC, fused
 // (third_party/tfluids.cc:859-915, 660-774).
-template <bool OURS>
+template <bool IS3D, typename FT, bool OURS>
 __global__ void k_advect_vel_pass2(const float* __restrict__ U, const float* __restrict__ fwd,
-                                   const float* __restrict__ flags, float* __restrict__ dst, float dt,
-                                   float strength, Geo g) {
+                                   const FT* __restrict__ flags, float* __restrict__ dst, float dt,
+                                   float strength, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const long long c = cell(g, k, j, i);
-  const float* fl = flags + b * g.n;
+  const int c = cell(g, k, j, i);
+  const FT* fl = flags + b * g.n;
   const float* ub = U + (long long)b * g.nc * g.n;
   const float* fb = fwd + (long long)b * g.nc * g.n;
   const bool border = on_border(g, k, j, i);
@@ -530,10 +554,12 @@ __global__ void k_advect_vel_pass2(const float* __restrict__ U, const float* __r
 // generic/tfluids.cu:1765-1821 in IEEE arithmetic.
 //   bit0: cell is border-or-obstacle (p = 0); bits1..6: neighbour -x,+x,-y,+y,-z,+z is obstacle.
 // ---------------------------------------------------------------------------------------
-__global__ void k_jacobi_mask(const float* __restrict__ flags, unsigned char* __restrict__ mask, Geo g) {
+template <bool IS3D, typename FT>
+__global__ void k_jacobi_mask(const FT* __restrict__ flags, unsigned char* __restrict__ mask, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
-  const float* fl = flags + b * g.n;
+  const FT* fl = flags + b * g.n;
   unsigned m = 0;
   if (on_border(g, k, j, i) || (flag_i(fl, g, k, j, i) & kObstacle)) {
     m = 1;
@@ -550,14 +576,16 @@ __global__ void k_jacobi_mask(const float* __restrict__ flags, unsigned char* __
   mask[b * g.n + cell(g, k, j, i)] = (unsigned char)m;
 }
 
+template <bool IS3D, typename FT>
 __global__ void k_jacobi_iter(const unsigned char* __restrict__ mask, const float* __restrict__ div,
-                              const float* __restrict__ prev, float* __restrict__ cur, Geo g) {
+                              const float* __restrict__ prev, float* __restrict__ cur, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const long long c = b * g.n + cell(g, k, j, i);
   const unsigned m = mask[c];
   if (m & 1) { cur[c] = 0.0f; return; }
-  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  const int sy = g.nx, sz = g.nx * g.ny;
   const float pc = __ldg(prev + c);
   float p1 = (m & 2) ? pc : __ldg(prev + c - 1);
   float p2 = (m & 4) ? pc : __ldg(prev + c + 1);
@@ -570,6 +598,62 @@ __global__ void k_jacobi_iter(const unsigned char* __restrict__ mask, const floa
   }
   const float denom = g.is3d ? 6.0f : 4.0f;
   cur[c] = (p1 + p2 + p3 + p4 + p5 + p6 + __ldg(div + c)) / denom;
+}
+
+// Same update, 4 consecutive x cells per thread (float4 rows, one 32-bit load for the 4 mask
+// bytes): 8 memory instructions per 4 cells instead of 40.  Requires nx % 4 == 0.
+template <bool IS3D, typename FT>
+__global__ void __launch_bounds__(256)
+k_jacobi_iter4(const unsigned char* __restrict__ mask, const float* __restrict__ div,
+               const float* __restrict__ prev, float* __restrict__ cur, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
+  const int nzr = g.zhi - g.zlo;
+  const int b = zz / nzr;
+  const int k = g.zlo + (zz - b * nzr);
+  if (i0 >= g.nx || j >= g.ny || b >= g.nb) return;
+  const long long c = b * g.n + cell(g, k, j, i0);
+  const unsigned m4 = __ldg((const unsigned*)(mask + c));
+  float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if ((m4 & 0x01010101u) != 0x01010101u) {          // at least one cell of the quad is live
+    const int sy = g.nx, sz = g.nx * g.ny;
+    const float4 pc = __ldg((const float4*)(prev + c));
+    const float4 dv = __ldg((const float4*)(div + c));
+    const float4 ym = __ldg((const float4*)(prev + c - sy));   // a live cell is never on the border,
+    const float4 yp = __ldg((const float4*)(prev + c + sy));   // so these rows exist
+    float4 zm = make_float4(0.f, 0.f, 0.f, 0.f), zp = zm;
+    if (g.is3d) {
+      zm = __ldg((const float4*)(prev + c - sz));
+      zp = __ldg((const float4*)(prev + c + sz));
+    }
+    const float left = i0 > 0 ? __ldg(prev + c - 1) : 0.0f;
+    const float right = i0 + 4 < g.nx ? __ldg(prev + c + 4) : 0.0f;
+    const float pcv[4] = {pc.x, pc.y, pc.z, pc.w};
+    const float xm[4] = {left, pc.x, pc.y, pc.z};
+    const float xp[4] = {pc.y, pc.z, pc.w, right};
+    const float ymv[4] = {ym.x, ym.y, ym.z, ym.w}, ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+    const float zmv[4] = {zm.x, zm.y, zm.z, zm.w}, zpv[4] = {zp.x, zp.y, zp.z, zp.w};
+    const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
+    const float denom = g.is3d ? 6.0f : 4.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned m = (m4 >> (8 * q)) & 0xFFu;
+      if (m & 1) continue;
+      const float p1 = (m & 2) ? pcv[q] : xm[q];
+      const float p2 = (m & 4) ? pcv[q] : xp[q];
+      const float p3 = (m & 8) ? pcv[q] : ymv[q];
+      const float p4 = (m & 16) ? pcv[q] : ypv[q];
+      float p5 = 0.0f, p6 = 0.0f;
+      if (g.is3d) {
+        p5 = (m & 32) ? pcv[q] : zmv[q];
+        p6 = (m & 64) ? pcv[q] : zpv[q];
+      }
+      out[q] = (p1 + p2 + p3 + p4 + p5 + p6 + dvv[q]) / denom;
+    }
+  }
+  *(float4*)(cur + c) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // sum over one batch element of (a - b)^2, accumulated in double: out[b] += ...
@@ -616,110 +700,142 @@ __global__ void k_clamp(float* __restrict__ x, float lo, float hi, long long n) 
 // ---------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------
-#define TFL_LAUNCH3(kernel, g, st, ...)            \
-  do {                                             \
-    dim3 grid_, block_;                            \
-    launch_dims(g, grid_, block_);                 \
-    kernel<<<grid_, block_, 0, st>>>(__VA_ARGS__); \
+// Launch `kernel<IS3D, FT, extra...>` with IS3D picked from the geometry.
+#define TFL_LAUNCH3(kernel, FT, g, st, ...)                      \
+  do {                                                           \
+    dim3 grid_, block_;                                          \
+    launch_dims(g, grid_, block_);                               \
+    if ((g).is3d) kernel<true, FT><<<grid_, block_, 0, st>>>(__VA_ARGS__);   \
+    else kernel<false, FT><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
+  } while (0)
+#define TFL_LAUNCH3X(kernel, FT, X, g, st, ...)                  \
+  do {                                                           \
+    dim3 grid_, block_;                                          \
+    launch_dims(g, grid_, block_);                               \
+    if ((g).is3d) kernel<true, FT, X><<<grid_, block_, 0, st>>>(__VA_ARGS__);   \
+    else kernel<false, FT, X><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
   } while (0)
 
 void launch_empty_domain(float* flags, const Geo& g, int bnd, cudaStream_t st) {
-  TFL_LAUNCH3(k_empty_domain, g, st, flags, g, bnd);
+  TFL_LAUNCH3(k_empty_domain, float, g, st, flags, g, bnd);
 }
 void launch_flags_to_occupancy(const float* flags, float* occ, long long n, unsigned long long* bad,
                                cudaStream_t st) {
   k_flags_to_occupancy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(flags, occ, n, bad);
 }
-void launch_set_wall_bcs(float* U, const float* flags, const Geo& g, int as_mask, cudaStream_t st) {
-  TFL_LAUNCH3(k_set_wall_bcs, g, st, U, flags, g, as_mask);
+template <typename FT>
+void launch_set_wall_bcs(float* U, const FT* flags, const Geo& g, int as_mask, cudaStream_t st) {
+  TFL_LAUNCH3(k_set_wall_bcs, FT, g, st, U, flags, g, as_mask);
 }
-void launch_divergence(const float* U, const float* flags, float* div, const Geo& g, cudaStream_t st) {
-  TFL_LAUNCH3(k_divergence, g, st, U, flags, div, g);
+template <typename FT>
+void launch_divergence(const float* U, const FT* flags, float* div, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_divergence, FT, g, st, U, flags, div, g);
 }
-void launch_velocity_update(float* U, const float* flags, const float* p, const Geo& g, cudaStream_t st) {
-  TFL_LAUNCH3(k_velocity_update, g, st, U, flags, p, g);
+template <typename FT>
+void launch_velocity_update(float* U, const FT* flags, const float* p, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_velocity_update, FT, g, st, U, flags, p, g);
 }
-void launch_add_buoyancy(float* U, const float* flags, const float* rho, const float s[3], const Geo& g,
+template <typename FT>
+void launch_add_buoyancy(float* U, const FT* flags, const float* rho, const float s[3], const Geo& g,
                          cudaStream_t st) {
-  TFL_LAUNCH3(k_add_buoyancy, g, st, U, flags, rho, s[0], s[1], s[2], g);
+  TFL_LAUNCH3(k_add_buoyancy, FT, g, st, U, flags, rho, s[0], s[1], s[2], g);
 }
-void launch_add_gravity(float* U, const float* flags, const float f[3], const Geo& g, cudaStream_t st) {
-  TFL_LAUNCH3(k_add_gravity, g, st, U, flags, f[0], f[1], f[2], g);
+template <typename FT>
+void launch_add_gravity(float* U, const FT* flags, const float f[3], const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_add_gravity, FT, g, st, U, flags, f[0], f[1], f[2], g);
 }
 void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st) {
   Geo g1 = g;
   g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
   g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
-  TFL_LAUNCH3(k_vort_curl, g1, st, U, curl, cnorm, g1);
+  TFL_LAUNCH3(k_vort_curl, float, g1, st, U, curl, cnorm, g1);
 }
-int launch_vorticity(float* U, const float* flags, float strength, float* curl, float* cnorm, const Geo& g,
+template <typename FT>
+int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, const Geo& g,
                      cudaStream_t st) {
   // curl / |curl| are needed one cell beyond the computed range in every direction
   // (confinement force at i-1 reads |curl| at i-2): widen the first pass in z.
   Geo g1 = g;
   g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
   g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
-  TFL_LAUNCH3(k_vort_curl, g1, st, U, curl, cnorm, g1);
-  TFL_LAUNCH3(k_vort_apply, g, st, U, flags, curl, cnorm, strength, g);
+  TFL_LAUNCH3(k_vort_curl, FT, g1, st, U, curl, cnorm, g1);
+  TFL_LAUNCH3(k_vort_apply, FT, g, st, U, flags, curl, cnorm, strength, g);
   return 2;
 }
 
-int launch_advect_scalar(float dt, const float* s, const float* U, const float* flags, int method,
+template <typename FT>
+int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, int method,
                          int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
                          const Geo& g_fwd, cudaStream_t st) {
   switch (method) {
     case TFL_ADVECT_EULER:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_EULER>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER, g, st, s, U, flags, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_EULER_OURS:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_EULER_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_RK2_OURS:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_RK2_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK2_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_RK3_OURS:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_RK3_OURS>, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK3_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_MACCORMACK:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_MACCORMACK>, g_fwd, st, s, U, flags, fwd, nullptr, dt, outside, g_fwd);
-      TFL_LAUNCH3(k_advect_scalar_pass2_manta, g, st, s, fwd, U, flags, dst, dt, strength, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK, g_fwd, st, s, U, flags, fwd, nullptr, dt, outside, g_fwd);
+      TFL_LAUNCH3(k_advect_scalar_pass2_manta, FT, g, st, s, fwd, U, flags, dst, dt, strength, g);
       return 2;
     case TFL_ADVECT_MACCORMACK_OURS:
-      TFL_LAUNCH3(k_advect_scalar_pass1<TFL_ADVECT_MACCORMACK_OURS>, g_fwd, st, s, U, flags, fwd, fwd_pos, dt, outside, g_fwd);
-      TFL_LAUNCH3(k_advect_scalar_pass2_ours, g, st, s, fwd, fwd_pos, U, flags, dst, dt, strength, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK_OURS, g_fwd, st, s, U, flags, fwd, fwd_pos, dt, outside, g_fwd);
+      TFL_LAUNCH3(k_advect_scalar_pass2_ours, FT, g, st, s, fwd, fwd_pos, U, flags, dst, dt, strength, outside, g);
       return 2;
   }
   return -1;
 }
 
-int launch_advect_vel(float dt, const float* U, const float* flags, int method, float strength, float* dst,
+template <typename FT>
+int launch_advect_vel(float dt, const float* U, const FT* flags, int method, float strength, float* dst,
                       float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st) {
   if (method == TFL_ADVECT_RK2_OURS || method == TFL_ADVECT_RK3_OURS) method = TFL_ADVECT_MACCORMACK_OURS;
   switch (method) {
     case TFL_ADVECT_EULER:
-      TFL_LAUNCH3(k_advect_vel_pass1<false>, g, st, U, flags, dst, dt, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g, st, U, flags, dst, dt, g);
       return 1;
     case TFL_ADVECT_EULER_OURS:
-      TFL_LAUNCH3(k_advect_vel_pass1<true>, g, st, U, flags, dst, dt, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g, st, U, flags, dst, dt, g);
       return 1;
     case TFL_ADVECT_MACCORMACK:
-      TFL_LAUNCH3(k_advect_vel_pass1<false>, g_fwd, st, U, flags, fwd, dt, g_fwd);
-      TFL_LAUNCH3(k_advect_vel_pass2<false>, g, st, U, fwd, flags, dst, dt, strength, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g_fwd, st, U, flags, fwd, dt, g_fwd);
+      TFL_LAUNCH3X(k_advect_vel_pass2, FT, false, g, st, U, fwd, flags, dst, dt, strength, g);
       return 2;
     case TFL_ADVECT_MACCORMACK_OURS:
-      TFL_LAUNCH3(k_advect_vel_pass1<true>, g_fwd, st, U, flags, fwd, dt, g_fwd);
-      TFL_LAUNCH3(k_advect_vel_pass2<true>, g, st, U, fwd, flags, dst, dt, strength, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g_fwd, st, U, flags, fwd, dt, g_fwd);
+      TFL_LAUNCH3X(k_advect_vel_pass2, FT, true, g, st, U, fwd, flags, dst, dt, strength, g);
       return 2;
   }
   return -1;
 }
 
-void launch_jacobi_mask(const float* flags, unsigned char* mask, const Geo& g, cudaStream_t st) {
-  TFL_LAUNCH3(k_jacobi_mask, g, st, flags, mask, g);
+template <typename FT>
+void launch_jacobi_mask(const FT* flags, unsigned char* mask, const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3(k_jacobi_mask, FT, g, st, flags, mask, g);
 }
 void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
                         const Geo& g, cudaStream_t st) {
-  TFL_LAUNCH3(k_jacobi_iter, g, st, mask, div, prev, cur, g);
+  const bool aligned = ((uintptr_t)mask % 4 == 0) && ((uintptr_t)div % 16 == 0) && ((uintptr_t)prev % 16 == 0) &&
+                       ((uintptr_t)cur % 16 == 0);
+  if (g.nx % 4 == 0 && aligned) {
+    const int nzr = g.zhi - g.zlo;
+    const int qx = g.nx / 4;
+    dim3 block(qx >= 32 ? 32 : qx, 1, 1);
+    block.y = g.nz == 1 ? 8 : 4;
+    block.z = g.nz == 1 ? 1 : 2;
+    dim3 grid((qx + block.x - 1) / block.x, (g.ny + block.y - 1) / block.y,
+              ((long long)g.nb * nzr + block.z - 1) / block.z);
+    if (g.is3d) k_jacobi_iter4<true, float><<<grid, block, 0, st>>>(mask, div, prev, cur, g);
+    else k_jacobi_iter4<false, float><<<grid, block, 0, st>>>(mask, div, prev, cur, g);
+    return;
+  }
+  TFL_LAUNCH3(k_jacobi_iter, float, g, st, mask, div, prev, cur, g);
 }
 void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st) {
   long long blocks = (n + 1023) / 1024;
@@ -731,6 +847,33 @@ void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, c
 }
 void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st) {
   k_clamp<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, lo, hi, n);
+}
+
+
+// Explicit instantiations: float flags (operator-level API) and byte flags (fused step).
+#define TFL_INSTANTIATE(FT)                                                                                   \
+  template void launch_set_wall_bcs<FT>(float*, const FT*, const Geo&, int, cudaStream_t);                    \
+  template void launch_divergence<FT>(const float*, const FT*, float*, const Geo&, cudaStream_t);            \
+  template void launch_velocity_update<FT>(float*, const FT*, const float*, const Geo&, cudaStream_t);       \
+  template void launch_add_buoyancy<FT>(float*, const FT*, const float*, const float*, const Geo&, cudaStream_t); \
+  template void launch_add_gravity<FT>(float*, const FT*, const float*, const Geo&, cudaStream_t);           \
+  template int launch_vorticity<FT>(float*, const FT*, float, float*, float*, const Geo&, cudaStream_t);     \
+  template int launch_advect_scalar<FT>(float, const float*, const float*, const FT*, int, int, float, float*, \
+                                        float*, float*, const Geo&, const Geo&, cudaStream_t);               \
+  template int launch_advect_vel<FT>(float, const float*, const FT*, int, float, float*, float*, const Geo&,  \
+                                     const Geo&, cudaStream_t);                                              \
+  template void launch_jacobi_mask<FT>(const FT*, unsigned char*, const Geo&, cudaStream_t);
+TFL_INSTANTIATE(float)
+TFL_INSTANTIATE(unsigned char)
+#undef TFL_INSTANTIATE
+
+// float flags -> byte flags (once per fused step).
+__global__ void k_flags_to_u8(const float* __restrict__ f, unsigned char* __restrict__ o, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) o[t] = (unsigned char)(((int)f[t]) & 0xFF);
+}
+void launch_flags_to_u8(const float* f, unsigned char* o, long long n, cudaStream_t st) {
+  k_flags_to_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, o, n);
 }
 
 }  // namespace tfl
