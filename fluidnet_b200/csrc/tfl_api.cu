@@ -573,6 +573,8 @@ int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
   return 0;
 }
 int tfl_cnn_get_mode(const tfl_cnn* m) { return m ? m->mode : -1; }
+// Undocumented debugging hook (not in tfl.h): per-CTA phase timestamps of the tensor-core conv.
+int tfl_debug_conv_timestamps(void* dev_buf) { conv_tc_set_debug((long long*)dev_buf); return 0; }
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   if (!m) return;

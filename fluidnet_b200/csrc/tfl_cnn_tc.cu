@@ -118,6 +118,8 @@ __device__ __forceinline__ float4 tf32_hi(float4 v) {
   return h;
 }
 
+__device__ long long* g_tc_dbg = nullptr;   // optional phase timestamps (tests/dbg only)
+
 template <int IN_PLANES, bool FINAL, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 2)
 k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __restrict__ p_net,
@@ -130,6 +132,7 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
   constexpr int B_GROUP_BYTES = 2 * NB * 16;
   constexpr int B_BYTES = kGroups * B_GROUP_BYTES;
   constexpr int COLS_PER_BUF = SPLIT ? 128 : 32;     // TMEM columns per accumulator buffer
+  constexpr int TMEM_COLS = 2 * COLS_PER_BUF;
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_BYTES;
   uint64_t* bars = (uint64_t*)(smem + A_BYTES + B_BYTES);   // full[2], empty[2]
@@ -138,19 +141,22 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tx = blockIdx.x, ty = blockIdx.y;
+  long long* dbg = g_tc_dbg;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (dbg && tid == 0) dbg[cta_lin * 8 + 0] = clock64();
   const int tzb = blockIdx.z % g.ntz, b = blockIdx.z / g.ntz;
 
   if (tid == 0) {
-    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[0]), 1);       // full[0], full[1]: one tcgen05.commit per batch
     mbar_init(smem_u32(&bars[1]), 1);
-    mbar_init(smem_u32(&bars[2]), 128);
+    mbar_init(smem_u32(&bars[2]), 128);     // empty[0], empty[1]: the owning epilogue warpgroup arrives
     mbar_init(smem_u32(&bars[3]), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(2 * COLS_PER_BUF));
+                 "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
 
@@ -159,33 +165,51 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
   const long long batch_g = plane_g * 2;
   const int x0 = tx * 30, y0 = ty * T::TY, z0 = tzb * T::TZ;                  // padded coords of box origin
   const float4* inb = in + b * batch_g;
-#pragma unroll 2
-  for (int idx = tid; idx < T::POS; idx += kThreads) {
-    const int l = idx & 31, r = idx >> 5;
-    const int yy = r % T::PY, zz = r / T::PY;
-    int gx = x0 + l, gy = y0 + yy, gz = z0 + zz;
-    const bool inside = gx < g.px && gy < g.py && gz < g.nz + 2;
-    gx = inside ? gx : 0; gy = inside ? gy : 0; gz = inside ? gz : 0;        // (0,0,0) is a zero border voxel
-    const long long go = ((long long)gz * g.py + gy) * g.px + gx;
-    if (!SPLIT) {
+  if (!SPLIT) {
+    for (int idx = tid; idx < T::POS; idx += kThreads) {
+      const int l = idx & 31, r = idx >> 5;
+      const int yy = r % T::PY, zz = r / T::PY;
+      int gx = x0 + l, gy = y0 + yy, gz = z0 + zz;
+      const bool inside = gx < g.px && gy < g.py && gz < g.nz + 2;
+      gx = inside ? gx : 0; gy = inside ? gy : 0; gz = inside ? gz : 0;      // (0,0,0) is a zero border voxel
+      const long long go = ((long long)gz * g.py + gy) * g.px + gx;
 #pragma unroll
       for (int h = 0; h < IN_PLANES; h++)
         cp_async16(smem_u32(sA + h * T::PLANE_BYTES + idx * 16), inb + h * plane_g + go);
       if (IN_PLANES == 1) *(float4*)(sA + T::PLANE_BYTES + idx * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      float4 v[IN_PLANES];
+    }
+  } else {
+    // 3xTF32: the hi/lo split happens in registers on the way in.  All loads are issued
+    // before the first use so that one memory round trip covers the whole box.
+    constexpr int PER = (T::POS + kThreads - 1) / kThreads;
+    float4 v[PER][IN_PLANES];
 #pragma unroll
-      for (int h = 0; h < IN_PLANES; h++) v[h] = __ldg(inb + h * plane_g + go);
+    for (int it = 0; it < PER; it++) {
+      const int idx = tid + it * kThreads;
+      const int l = idx & 31, r = idx >> 5;
+      const int yy = r % T::PY, zz = r / T::PY;
+      int gx = x0 + l, gy = y0 + yy, gz = z0 + zz;
+      const bool inside = idx < T::POS && gx < g.px && gy < g.py && gz < g.nz + 2;
+      gx = inside ? gx : 0; gy = inside ? gy : 0; gz = inside ? gz : 0;
+      const long long go = ((long long)gz * g.py + gy) * g.px + gx;
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
-        if (h < IN_PLANES) {
-          hi = tf32_hi(v[h < IN_PLANES ? h : 0]);
-          const float4 w = v[h < IN_PLANES ? h : 0];
-          lo = make_float4(w.x - hi.x, w.y - hi.y, w.z - hi.z, w.w - hi.w);
+      for (int h = 0; h < IN_PLANES; h++) v[it][h] = __ldg(inb + h * plane_g + go);
+    }
+#pragma unroll
+    for (int it = 0; it < PER; it++) {
+      const int idx = tid + it * kThreads;
+      if (idx < T::POS) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+          if (h < IN_PLANES) {
+            const float4 w = v[it][h < IN_PLANES ? h : 0];
+            hi = tf32_hi(w);
+            lo = make_float4(w.x - hi.x, w.y - hi.y, w.z - hi.z, w.w - hi.w);
+          }
+          *(float4*)(sA + h * T::PLANE_BYTES + idx * 16) = hi;
+          *(float4*)(sA + (2 + h) * T::PLANE_BYTES + idx * 16) = lo;
         }
-        *(float4*)(sA + h * T::PLANE_BYTES + idx * 16) = hi;
-        *(float4*)(sA + (2 + h) * T::PLANE_BYTES + idx * 16) = lo;
       }
     }
   }
@@ -199,6 +223,7 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && tid == 0) { dbg[cta_lin * 8 + 1] = clock64(); unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); dbg[cta_lin * 8 + 7] = smid; }
 
   if (warp == 8) {
     // ===== MMA issuer: one elected thread =====
@@ -206,29 +231,35 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       constexpr uint32_t IDESC_MAIN = make_idesc(128, NB);
       constexpr uint32_t IDESC_LO = make_idesc(128, 32);
+      // Descriptors are loop invariant up to a start-address offset per M tile: build them once
+      // so that the issue loop is one 32-bit add + one tcgen05.mma per instruction.
+      uint64_t db[kGroups], da0[kGroups];
+#pragma unroll
+      for (int gi = 0; gi < kGroups; gi++) {
+        const int dz = gi / 3 - 1, dy = gi % 3 - 1;
+        db[gi] = make_desc(sB_u + gi * B_GROUP_BYTES, NB * 16, 128);
+        da0[gi] = make_desc(sA_u + (uint32_t)((((1 + dz) * T::PY + (1 + dy)) * kTX) * 16), T::PLANE_BYTES, 128);
+      }
+      constexpr uint32_t LO_PLANES_16 = (uint32_t)(2 * T::PLANE_BYTES) >> 4;
       for (int t = 0; t < T::MTILES; t++) {
         const int buf = t & 1;
         if (t >= 2) {
           mbar_wait(smem_u32(&bars[2 + buf]), (uint32_t)(((t >> 1) - 1) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        // M tile t: padded plane zp, rows yp .. yp+3, positions 0..31.
-        const int zp = 1 + t / T::RB, yp = 1 + 4 * (t % T::RB);
+        // M tile t: padded plane 1 + t / RB, rows 1 + 4 * (t % RB) .. +3, positions 0..31.
+        const uint32_t toff16 = (uint32_t)((((t / T::RB) * T::PY + 4 * (t % T::RB)) * kTX));   // 16-byte units
         const uint32_t d_addr = tmem_base + (uint32_t)(buf * COLS_PER_BUF);
 #pragma unroll
         for (int gi = 0; gi < kGroups; gi++) {
-          const int dz = gi / 3 - 1, dy = gi % 3 - 1;
-          const uint32_t a_off = (uint32_t)((((zp + dz) * T::PY + (yp + dy)) * kTX) * 16);
-          const uint64_t db = make_desc(sB_u + gi * B_GROUP_BYTES, NB * 16, 128);
-          const uint64_t da = make_desc(sA_u + a_off, T::PLANE_BYTES, 128);
-          umma_tf32(d_addr, da, db, IDESC_MAIN, gi > 0 ? 1u : 0u);
-          if (SPLIT) {
-            const uint64_t dal = make_desc(sA_u + 2 * T::PLANE_BYTES + a_off, T::PLANE_BYTES, 128);
-            umma_tf32(d_addr + 64, dal, db, IDESC_LO, gi > 0 ? 1u : 0u);
-          }
+          const uint64_t da = da0[gi] + toff16;
+          umma_tf32(d_addr, da, db[gi], IDESC_MAIN, gi > 0 ? 1u : 0u);
+          if (SPLIT) umma_tf32(d_addr + 64, da + LO_PLANES_16, db[gi], IDESC_LO, gi > 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&bars[buf]));
+        if (dbg && t == 0) dbg[cta_lin * 8 + 2] = clock64();
       }
+      if (dbg) dbg[cta_lin * 8 + 3] = clock64();
     }
   } else {
     // ===== epilogue warpgroups: warpgroup wg owns accumulator buffer wg (tiles t = wg, wg+2, ...) =====
@@ -237,6 +268,7 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
     for (int t = wg; t < T::MTILES; t += 2) {
       mbar_wait(smem_u32(&bars[wg]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg && tid == 0 && t == 0) dbg[cta_lin * 8 + 4] = clock64();
       const uint32_t taddr = tmem_base + (uint32_t)(wg * COLS_PER_BUF) + ((uint32_t)(q * 32) << 16);
       uint32_t r0[24];
       tmem_ld8(taddr + 0, r0);
@@ -310,8 +342,9 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (dbg && tid == 0) dbg[cta_lin * 8 + 5] = clock64();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * COLS_PER_BUF));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -350,6 +383,8 @@ ConvTcGeo make_conv_tc_geo(int nb, int nz, int ny, int nx) {
 size_t conv_tc_act_bytes(const ConvTcGeo& g) {
   return (size_t)g.nb * 2 * (g.nz + 2) * g.py * g.px * 16;
 }
+void conv_tc_set_debug(long long* dev_buf) { cudaMemcpyToSymbol(g_tc_dbg, &dev_buf, sizeof(dev_buf)); }
+
 int conv_tc_b_floats(int split) { return kGroups * 2 * (split ? 48 : 32) * 4; }
 
 // Host-side packing of one layer's weights [cout=8][cin][3][3][3] into the B operand blocks

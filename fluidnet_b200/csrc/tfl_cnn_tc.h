@@ -15,6 +15,7 @@ ConvTcGeo make_conv_tc_geo(int nb, int nz, int ny, int nx);
 // bytes of one activation buffer: [b][2 planes][nz+2][py][px] float4
 size_t conv_tc_act_bytes(const ConvTcGeo& g);
 int conv_tc_b_floats(int split);
+void conv_tc_set_debug(long long* dev_buf);   // nullptr disables
 void conv_tc_pack_weights(const float* w /*[8][cin][3][3][3]*/, int cin, int split, float* out);
 // in/out: padded channels-last activations; p_net: plain [b][z][y][x] (final layer only);
 // tail (final layer): w4[8][8] (o, c), b4[8], w5[8], b5[1] on the device.
