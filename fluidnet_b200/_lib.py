@@ -33,7 +33,7 @@ class State(C.Structure):
 SYMBOLS = [
     "tfl_advect_method_from_string", "tfl_create", "tfl_destroy", "tfl_last_error", "tfl_version",
     "tfl_set_stream", "tfl_get_stream", "tfl_sync", "tfl_trace_faults", "tfl_launch_count",
-    "tfl_set_slab", "tfl_alloc", "tfl_free", "tfl_alloc_host", "tfl_free_host", "tfl_memcpy_h2d",
+    "tfl_set_slab", "tfl_set_slab_margin", "tfl_cnn_stats", "tfl_cnn_project_from_sums", "tfl_alloc", "tfl_free", "tfl_alloc_host", "tfl_free_host", "tfl_memcpy_h2d",
     "tfl_memcpy_d2h", "tfl_memcpy_d2d", "tfl_advect_scalar", "tfl_advect_vel",
     "tfl_set_wall_bcs_forward", "tfl_velocity_divergence_forward", "tfl_velocity_update_forward",
     "tfl_add_buoyancy", "tfl_add_gravity", "tfl_vorticity_confinement",
@@ -68,6 +68,7 @@ def load():
     lib.tfl_launch_count.argtypes = [C.c_void_p]
     lib.tfl_trace_faults.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     lib.tfl_set_slab.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.tfl_set_slab_margin.argtypes = [C.c_void_p, C.c_int32]
     G = C.POINTER(Grid)
     lib.tfl_advect_scalar.argtypes = [C.c_void_p, C.c_float, G, G, G, C.c_int, C.c_int, C.c_float, G]
     lib.tfl_advect_vel.argtypes = [C.c_void_p, C.c_float, G, G, C.c_int, C.c_float, G]
@@ -92,6 +93,8 @@ def load():
     lib.tfl_cnn_get_mode.argtypes = [C.c_void_p]
     lib.tfl_cnn_project.argtypes = [C.c_void_p, C.c_void_p, G, G, G, G, G, C.c_float,
                                     C.POINTER(C.c_float)]
+    lib.tfl_cnn_stats.argtypes = [C.c_void_p, G, G, G, C.c_void_p]
+    lib.tfl_cnn_project_from_sums.argtypes = [C.c_void_p, C.c_void_p, G, G, G, C.c_void_p, G, G, C.c_float]
     lib.tfl_simulate_step.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(MConf), C.c_void_p]
     lib.tfl_host_sim_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -29,6 +29,7 @@ struct tfl_ctx {
   long long launches = 0;
   bool slab = false;
   int zoff = 0, gnz = 0, zlo = 0, zhi = 0;
+  int slab_margin = 2;                      // extra planes on which forward passes are evaluated
 };
 
 struct tfl_cnn {
@@ -140,6 +141,17 @@ int make_geo(tfl_ctx* ctx, const tfl_grid* flags, int is3d, Geo* g) {
   return 0;
 }
 
+// z-slab mode: the MacCormack forward pass must also cover the planes the backward traces of the
+// owned planes can reach (margin), but never start a trace on a local end plane that is not a
+// global end (the MAC samples reach one plane further).
+void widen_for_forward_pass(const tfl_ctx* ctx, const Geo& g, Geo* gf) {
+  if (!ctx->slab) { gf->zlo = 0; gf->zhi = g.nz; return; }
+  const int lo_lim = (g.zoff == 0) ? 0 : 1;
+  const int hi_lim = (g.zoff + g.nz == g.gnz) ? g.nz : g.nz - 1;
+  gf->zlo = std::max(lo_lim, g.zlo - ctx->slab_margin);
+  gf->zhi = std::min(hi_lim, g.zhi + ctx->slab_margin);
+}
+
 float get_dx(const Geo& g) {     // third_party/grid.cc:37-40 on the GLOBAL grid
   int m = g.nx > g.ny ? g.nx : g.ny;
   if (g.gnz > m) m = g.gnz;
@@ -230,6 +242,12 @@ int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo
   if (global_nz <= 0) { ctx->slab = false; return 0; }
   ctx->slab = true;
   ctx->zoff = z_offset; ctx->gnz = global_nz; ctx->zlo = z_lo; ctx->zhi = z_hi;
+  return 0;
+}
+
+int tfl_set_slab_margin(tfl_ctx* ctx, int32_t planes) {
+  if (planes < 0) return fail(ctx, "slab margin must be >= 0");
+  ctx->slab_margin = planes;
   return 0;
 }
 
@@ -383,8 +401,8 @@ int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid*
   float* fwd_pos = cv.take<float>(cells * g.nc);
   float* tmp = cv.take<float>(cells);
   float* dst = in_place ? tmp : s_dst->data;
-  Geo gf = g;     // forward pass over every local plane (its halo planes feed the backward pass)
-  gf.zlo = 0; gf.zhi = g.nz;
+  Geo gf = g;     // forward pass on a wider range: its halo planes feed the backward pass
+  widen_for_forward_pass(ctx, g, &gf);
   const int nl = launch_advect_scalar(dt, s->data, U->data, flags->data, method, sample_outside_fluid,
                                       strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectScalar: bad method");
@@ -416,12 +434,7 @@ int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* fl
   float* tmp = cv.take<float>(cells * g.nc);
   float* dst = in_place ? tmp : U_dst->data;
   Geo gf = g;
-  gf.zlo = 0; gf.zhi = g.nz;
-  if (ctx->slab) {     // the MAC samples reach one plane below: never start a trace on local plane 0 / nz-1
-    gf.zlo = 1; gf.zhi = g.nz - 1;
-    if (g.zoff == 0) gf.zlo = 0;
-    if (g.zoff + g.nz == g.gnz) gf.zhi = g.nz;
-  }
+  widen_for_forward_pass(ctx, g, &gf);
   const int nl = launch_advect_vel(dt, U->data, flags->data, method, strength, dst, fwd, g, gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectVel: bad method");
   ctx->launches += nl;
@@ -620,7 +633,7 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   double* sums = ctx->dscratch + 64;
   cudaStream_t st = ctx->stream;
   TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
-  launch_cnn_mask_stats(U_div, flags, U1, sums, g, st);
+  launch_cnn_mask_stats(U_div, flags, U1, sums, g.zlo, g.zhi, g, st);
   launch_cnn_scale(sums, scale, g.nb, (long long)g.nc * g.n, threshold, st);
   if (m->mode > 0 && m->tc_ok && !ctx->slab) {
     if (cnn_ensure_act(ctx, m, g)) return 1;
@@ -682,6 +695,65 @@ int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_g
     TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return 0;
+}
+
+// z-slab variant of model:forward, split around the one global reduction (the input scale):
+//   tfl_cnn_stats              U1 = SetWallBcs mask * U on every local plane where the mask is
+//                              computable, and (sum, sum of squares) over the OWNED planes into
+//                              dev_sums[2 * nb] (device doubles the caller all-reduces, e.g. with NCCL);
+//   tfl_cnn_project_from_sums  everything after the reduction.  The conv stack runs on the whole
+//                              local slab (halo planes included), so results are valid on planes at
+//                              least 4 planes away from a local end that is not a global end.
+int tfl_cnn_stats(tfl_ctx* ctx, const tfl_grid* U_div, const tfl_grid* flags, const tfl_grid* U1,
+                  double* dev_sums) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U_div, flags) || check_vel(ctx, U1, flags)) return 1;
+  if (!dev_sums) return fail(ctx, "cnn_stats: nil sums");
+  Geo g;
+  if (make_geo(ctx, flags, U_div->nc == 3, &g)) return 1;
+  Geo gw = g;
+  if (ctx->slab) {
+    gw.zlo = (g.zoff == 0) ? 0 : 1;
+    gw.zhi = (g.zoff + g.nz == g.gnz) ? g.nz : g.nz - 1;
+  }
+  TFL_CUDA(ctx, cudaMemsetAsync(dev_sums, 0, sizeof(double) * 2 * g.nb, ctx->stream));
+  launch_cnn_mask_stats(U_div->data, flags->data, U1->data, dev_sums, g.zlo, g.zhi, gw, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "cnn_stats");
+}
+
+int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_grid* U1,
+                              const tfl_grid* flags, const double* dev_sums, const tfl_grid* p_out,
+                              const tfl_grid* U_out, float threshold) {
+  if (!m) return fail(ctx, "cnn is nil");
+  if (!m->tc_ok || m->mode == 0) return fail(ctx, "cnn_project_from_sums needs the tensor-core path (3-D default net)");
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U1, flags) ||
+      check_scalar(ctx, p_out, "p") || check_vel(ctx, U_out, flags))
+    return 1;
+  Geo g;
+  if (make_geo(ctx, flags, 1, &g)) return 1;
+  if (cnn_ensure_act(ctx, m, g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  if (arena_reserve(ctx, carve_bytes({cells * 4, 4 * (size_t)g.nb}))) return 1;
+  Carver cv(ctx);
+  float* p_net = cv.take<float>(cells);
+  float* scale = cv.take<float>(g.nb);
+  cudaStream_t st = ctx->stream;
+  // scale from the (already reduced) sums; the sample count is that of the GLOBAL grid.
+  launch_cnn_scale(dev_sums, scale, g.nb, (long long)g.nc * g.nx * g.ny * g.gnz, threshold, st);
+  Geo gi = g;            // the divergence reads U1 one plane up
+  if (ctx->slab) {
+    gi.zlo = (g.zoff == 0) ? 0 : 1;
+    gi.zhi = (g.zoff + g.nz == g.gnz) ? g.nz : g.nz - 2;
+  }
+  const ConvTcGeo& tg = m->act_geo;
+  const int split = m->mode == 2 ? 1 : 0;
+  launch_cnn_inputs_padded(p_div->data, U1->data, flags->data, scale, m->act[0], tg.px, tg.py, gi, st);
+  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
+  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
+  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+  launch_cnn_finish(p_net, U1->data, flags->data, scale, p_out->data, U_out->data, g, st);
+  ctx->launches += 6;
+  return check_launch(ctx, "cnn_project_from_sums");
 }
 
 // ---------------------------------------------------------------------------------------

@@ -43,8 +43,8 @@ void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, c
 void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st);
 
 // CNN pre/post stages (exact float semantics of lib/model.lua's non-conv nodes).
-void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, const Geo& g,
-                           cudaStream_t st);
+void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, int own_lo, int own_hi,
+                           const Geo& g, cudaStream_t st);
 void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_batch, float threshold,
                       cudaStream_t st);
 void launch_cnn_inputs(const float* p_div, const float* U1, const float* flags, const float* scale,

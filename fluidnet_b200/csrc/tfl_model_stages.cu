@@ -12,7 +12,7 @@ namespace tfl {
 // U1 = U * wallmask; sums[b] += (sum U1, sum U1^2) over the launch range (double).
 template <bool IS3D, typename FT>
 __global__ void k_cnn_mask_stats(const float* __restrict__ U, const FT* __restrict__ flags,
-                                 float* __restrict__ U1, double* __restrict__ sums, Geo gin) {
+                                 float* __restrict__ U1, double* __restrict__ sums, int own_lo, int own_hi, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   const bool live = thread_cell(g, b, k, j, i);
@@ -25,9 +25,11 @@ __global__ void k_cnn_mask_stats(const float* __restrict__ U, const FT* __restri
       float u = U[c + a * g.n];
       if (z[a]) u = u * 0.0f;
       U1[c + a * g.n] = u;
-      const float sq = u * u;
-      s += (double)u;
-      ss += (double)sq;
+      if (k >= own_lo && k < own_hi) {      // the statistics cover owned planes only (z-slabs)
+        const float sq = u * u;
+        s += (double)u;
+        ss += (double)sq;
+      }
     }
   }
   // One block never straddles two batch entries unless nb > 1 and the z range is odd; in that
@@ -152,9 +154,9 @@ __global__ void k_cnn_finish(const float* __restrict__ p_net, const float* __res
     else kernel<false, float><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
   } while (0)
 
-void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, const Geo& g,
-                           cudaStream_t st) {
-  TFL_LAUNCH3B(k_cnn_mask_stats, g, st, U, flags, U1, sums, g);
+void launch_cnn_mask_stats(const float* U, const float* flags, float* U1, double* sums, int own_lo, int own_hi,
+                           const Geo& g, cudaStream_t st) {
+  TFL_LAUNCH3B(k_cnn_mask_stats, g, st, U, flags, U1, sums, own_lo, own_hi, g);
 }
 void launch_cnn_scale(const double* sums, float* scale, int nb, long long n_per_batch, float threshold,
                       cudaStream_t st) {

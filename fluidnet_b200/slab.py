@@ -1,0 +1,187 @@
+"""z-slab decomposition of ONE fluid domain across the GPUs of a node.
+
+The reference is single-GPU; this is the multi-GPU path north_star asks for: rank r owns the planes
+[z0, z1) of every field plus `halo` ghost planes on each interior side, the kernels of libtfl.so
+are told where the local array sits in the global grid (tfl_set_slab: border tests, getDx, line
+traces and interpolation clamps use GLOBAL coordinates), and ghost planes are refreshed with
+neighbour send/recv pairs (torch.distributed, NCCL over NVLink on GPUs, gloo in the CPU tests)
+before each phase whose stencil reaches across the cut:
+
+    exchange U, density  (halo)   -> advectScalar, advectVel   (MacCormack fwd pass evaluated on
+                                                                 owned +- margin planes, bwd on owned)
+    exchange U, density  (3)      -> addBuoyancy (-1), vorticityConfinement (-3 / +3)
+    exchange U, p        (5)      -> CNN projection: wall mask + sum/sumsq on owned planes,
+                                     all-reduce of the two sums (the input scale), conv stack on the
+                                     whole local slab, velocity update on owned planes
+
+There is no data-path collective other than those neighbour exchanges and the 2-double all-reduce.
+A line trace or stencil that leaves the local slab (halo too small for the velocity) increments
+the library's fault counter instead of reading out of bounds; `SlabSimulator.check()` raises.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+class SlabDecomposition:
+    """Which global planes a rank owns / stores, and the halo exchange between neighbours."""
+
+    def __init__(self, gnz, rank, world, halo):
+        assert world >= 1 and 0 <= rank < world
+        base, rem = divmod(gnz, world)
+        sizes = [base + (1 if r < rem else 0) for r in range(world)]
+        assert min(sizes) >= max(halo, 1), "slab thinner than the halo: use fewer ranks or a smaller halo"
+        self.gnz, self.rank, self.world, self.halo = gnz, rank, world, halo
+        self.z0 = sum(sizes[:rank])
+        self.z1 = self.z0 + sizes[rank]
+        self.lo_halo = min(halo, self.z0)                 # no ghost planes beyond the global ends
+        self.hi_halo = min(halo, gnz - self.z1)
+        self.zoff = self.z0 - self.lo_halo                # global index of local plane 0
+        self.nz = (self.z1 - self.z0) + self.lo_halo + self.hi_halo
+        self.own_lo = self.lo_halo
+        self.own_hi = self.lo_halo + (self.z1 - self.z0)
+
+    def scatter(self, t):
+        """Local slab (owned + ghost planes) of a global [b][c][gnz][y][x] tensor."""
+        return t[:, :, self.zoff:self.zoff + self.nz].contiguous()
+
+    def owned(self, t):
+        return t[:, :, self.own_lo:self.own_hi]
+
+    def exchange(self, tensors, width, group=None):
+        """Refresh `width` ghost planes on both sides of every tensor from the neighbours' owned
+        planes.  One packed message per neighbour and direction."""
+        if self.world == 1 or width == 0:
+            return
+        assert width <= self.halo
+        ops, unpack = [], []
+
+        def pack(a, b):
+            return torch.cat([t[:, :, a:b].reshape(-1) for t in tensors])
+
+        def plan(peer, send_rng, recv_rng):
+            sbuf = pack(*send_rng)
+            rbuf = torch.empty_like(sbuf)
+            ops.append(dist.P2POp(dist.isend, sbuf, peer, group))
+            ops.append(dist.P2POp(dist.irecv, rbuf, peer, group))
+            unpack.append((rbuf, recv_rng))
+
+        if self.rank > 0:                                  # lower neighbour: my first owned planes go down
+            plan(self.rank - 1, (self.own_lo, self.own_lo + width), (self.own_lo - width, self.own_lo))
+        if self.rank < self.world - 1:                     # upper neighbour
+            plan(self.rank + 1, (self.own_hi - width, self.own_hi), (self.own_hi, self.own_hi + width))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for rbuf, (a, b) in unpack:
+            off = 0
+            for t in tensors:
+                view = t[:, :, a:b]
+                n = view.numel()
+                view.copy_(rbuf[off:off + n].view(view.shape))
+                off += n
+
+
+class SlabSimulator:
+    """tfluids.simulate (convnet path) for one domain split in z across the ranks of `group`."""
+
+    def __init__(self, batch, mconf, model_layers, device, rank=None, world=None, margin=2, group=None):
+        """batch: dict of GLOBAL torch CPU tensors (pDiv, UDiv, flags, density and the BC arrays),
+        identical on every rank.  margin: planes a backward trace may reach (ceil(max|u| dt) + 1)."""
+        from . import tfluids, model as fmodel
+        self.tfluids = tfluids
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.mconf = dict(mconf)
+        assert (self.mconf.get("simMethod") or "convnet") == "convnet"
+        gnz = batch["flags"].shape[2]
+        self.dec = SlabDecomposition(gnz, self.rank, self.world, halo=2 * margin + 2)
+        self.margin = margin
+        self.device = torch.device(device)
+        self.s = {k: self.dec.scatter(v).to(self.device) for k, v in batch.items() if v is not None}
+        self.ctx = tfluids.context(self.device)
+        self.model = fmodel.ProjectionModel(model_layers, True, device=self.device,
+                                            normalizeInputThreshold=self.mconf.get("normalizeInputThreshold", 1e-5))
+        self.U1 = torch.empty_like(self.s["UDiv"])
+        self.sums = torch.zeros(2, dtype=torch.float64, device=self.device)
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _slab_on(self):
+        d = self.dec
+        self.ctx.set_slab(d.zoff, d.gnz, d.own_lo, d.own_hi)
+        self.ctx.check(self.ctx.lib.tfl_set_slab_margin(self.ctx.h, self.margin))
+
+    def _slab_off(self):
+        self.ctx.clear_slab()
+
+    def _bc(self):
+        t, s = self.tfluids, self.s
+        if s.get("UBC") is not None:
+            t.applyBC(s["UDiv"], s["UBCInvMask"], s["UBC"])
+        if s.get("densityBC") is not None:
+            t.applyBC(s["density"], s["densityBCInvMask"], s["densityBC"])
+
+    def step(self):
+        t, s, m, d = self.tfluids, self.s, self.mconf, self.dec
+        p, U, flags, rho = s["pDiv"], s["UDiv"], s["flags"], s["density"]
+        method, strength = m.get("advectionMethod"), m.get("maccormackStrength")
+        d.exchange([U, rho], d.halo, self.group)
+        self._slab_on()
+        t.advectScalar(m["dt"], rho, U, flags, method, None, False, strength)
+        t.advectVel(m["dt"], U, flags, method, None, strength)
+        self._slab_off()
+        self._bc()
+        d.exchange([U, rho], 3, self.group)
+        self._slab_on()
+        dx = 1.0 / max(d.gnz, flags.size(3), flags.size(4))
+        if m.get("buoyancyScale", 0) > 0:
+            k = torch.tensor(-(dx / 4) * m["buoyancyScale"], dtype=torch.float32).item()
+            g = m.get("gravity") or [0.0, 1.0, 0.0]
+            gv = [torch.tensor(float(v), dtype=torch.float32).item() * k for v in g]
+            gv = [torch.tensor(v, dtype=torch.float32).item() for v in gv]
+            t.addBuoyancy(U, flags, rho, gv, m["dt"])
+        if m.get("vorticityConfinementAmp", 0) > 0:
+            t.vorticityConfinement(U, flags, dx * m["vorticityConfinementAmp"])
+        self._slab_off()
+        self._bc()
+        d.exchange([U, p], 5, self.group)
+        self._slab_on()
+        c, lib = self.ctx, self.ctx.lib
+        c.use_current_stream()
+        c.check(lib.tfl_cnn_stats(c.h, t._grid(U), t._grid(flags), t._grid(self.U1), C.c_void_p(self.sums.data_ptr())))
+        if self.world > 1:
+            dist.all_reduce(self.sums, group=self.group)
+        c.check(lib.tfl_cnn_project_from_sums(c.h, self.model.h, t._grid(p), t._grid(self.U1), t._grid(flags),
+                                              C.c_void_p(self.sums.data_ptr()), t._grid(p), t._grid(U),
+                                              float(self.model.threshold)))
+        self._slab_off()
+        self._bc()
+        t.clamp(U, -1e6, 1e6)
+
+    def check(self):
+        """Raises if any stencil / trace left the local slab since the last check."""
+        f = torch.tensor([self.ctx.trace_faults()], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(f, group=self.group)
+        if f.item() != 0:
+            raise RuntimeError("z-slab halo too small for the current velocities (%d faults): raise `margin`"
+                               % int(f.item()))
+
+    def gather(self, key):
+        """Global tensor assembled from every rank's owned planes (on every rank, CPU)."""
+        mine = self.dec.owned(self.s[key]).contiguous()
+        if self.world == 1:
+            return mine.cpu()
+        sizes = [SlabDecomposition(self.dec.gnz, r, self.world, self.dec.halo) for r in range(self.world)]
+        parts = [torch.empty(mine.shape[:2] + (q.z1 - q.z0,) + mine.shape[3:], dtype=mine.dtype, device=mine.device)
+                 for q in sizes]
+        dist.all_gather(parts, mine, group=self.group) if len({tuple(x.shape) for x in parts}) == 1 else \
+            self._all_gather_uneven(parts, mine)
+        return torch.cat([x.cpu() for x in parts], dim=2)
+
+    def _all_gather_uneven(self, parts, mine):
+        for r in range(self.world):
+            if r == self.rank:
+                parts[r].copy_(mine)
+            dist.broadcast(parts[r], src=r, group=self.group)

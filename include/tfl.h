@@ -81,6 +81,9 @@ int64_t tfl_launch_count(const tfl_ctx* ctx);
  * domain with `global_nz` planes; operators compute local planes [z_lo, z_hi).
  * tfl_set_slab(ctx, 0, 0, 0, 0) restores single-domain behaviour. */
 int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo, int32_t z_hi);
+/* Planes beyond [z_lo, z_hi) on which the MacCormack forward passes are also evaluated (they feed
+ * the backward traces of the owned planes); default 2 = traces shorter than one cell. */
+int tfl_set_slab_margin(tfl_ctx* ctx, int32_t planes);
 
 /* ---- memory helpers (optional; callers may bring their own device pointers) ----------- */
 int tfl_alloc(tfl_ctx* ctx, size_t bytes, void** dev_ptr);
@@ -159,6 +162,17 @@ int tfl_cnn_get_mode(const tfl_cnn* cnn);
 int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* cnn, const tfl_grid* p_div, const tfl_grid* U_div,
                     const tfl_grid* flags, const tfl_grid* p_out, const tfl_grid* U_out,
                     float threshold, float* scale_out);
+
+/* z-slab variant of model:forward, split around its one global reduction (the input scale):
+ * tfl_cnn_stats writes U1 = wall-mask * U and the (sum, sum of squares) of U1 over the OWNED planes
+ * into dev_sums[2 * nb] (device doubles, to be all-reduced by the caller, e.g. NCCL);
+ * tfl_cnn_project_from_sums does the rest.  The conv stack runs on the whole local slab, so results
+ * are exact on planes >= 4 planes away from a local end that is not a global end. */
+int tfl_cnn_stats(tfl_ctx* ctx, const tfl_grid* U_div, const tfl_grid* flags, const tfl_grid* U1,
+                  double* dev_sums);
+int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* cnn, const tfl_grid* p_div, const tfl_grid* U1,
+                              const tfl_grid* flags, const double* dev_sums, const tfl_grid* p_out,
+                              const tfl_grid* U_out, float threshold);
 
 /* ---- the whole step: tfluids.simulate (lib/simulate.lua:175-327) ----------------------- */
 typedef struct tfl_mconf {        /* keys the loop reads (lib/simulate.lua:188-291) */
