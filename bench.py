@@ -159,6 +159,61 @@ def run_reference(args):
     return 0
 
 
+def run_slab(args, world, rank, local):
+    """BASELINE config 5: one domain split in z across the ranks (fluidnet_b200.slab)."""
+    import torch
+    import torch.distributed as dist
+    from fluidnet_b200.slab import SlabSimulator
+    n = args.grid
+    batch_np, mconf, mnp = make_problem(n)
+    tb = {k: torch.from_numpy(v) for k, v in batch_np.items()}
+    sim = SlabSimulator(tb, mconf, mnp["layers"], torch.device("cuda", local), rank, world)
+    del tb
+    for _ in range(max(args.warmup, 3)):
+        sim.step()
+    sim.check()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = sim.ctx.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        sim.step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = sim.ctx.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        sampler.stop_flag.set()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sim.check()
+    if rank == 0:
+        ms = t.item() / args.steps
+        halo_bytes = (2 * (4 * 6 + 4 * 4 + 4 * 5)) * n * n * 4 if world > 1 else 0
+        print(json.dumps({
+            "metric": "sim steps/sec on %d^3 MAC grid (CNN proj), one domain z-slab decomposed" % n,
+            "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ONE 3D %d^3 MAC grid split in z over %d GPU(s): maccormackOurs advection + plume "
+                                   "BCs + buoyancy + vorticity confinement + CNN projection; 3 neighbour halo "
+                                   "exchanges (widths 6/4/5 planes) + one 2-double all-reduce per step" % (n, world),
+                       "grid": [n, n, n], "parallelism": "z-slab x%d, NCCL send/recv halos" % world,
+                       "halo_bytes_per_rank_step": halo_bytes,
+                       "l2": "working set %d MB per rank > L2 at 256^3; no flush between steps" % (60 * (n / 128.0) ** 3 / world)},
+            "gpu_launches": int(launches), "clocks": sampler.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +222,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, default=N_GRID)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="grids", choices=["grids", "slab"],
+                    help="grids: one independent --grid^3 domain per GPU (weak scaling, the default and the "
+                         "BASELINE metric); slab: ONE --grid^3 domain z-slab decomposed over the GPUs with NCCL "
+                         "halo exchange (strong scaling, BASELINE config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,6 +241,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.grid
+    if args.mode == "slab":
+        return run_slab(args, world, rank, local)
     batch_np, mconf, mnp = make_problem(n)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):

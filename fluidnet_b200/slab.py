@@ -9,7 +9,7 @@ before each phase whose stencil reaches across the cut:
 
     exchange U, density  (halo)   -> advectScalar, advectVel   (MacCormack fwd pass evaluated on
                                                                  owned +- margin planes, bwd on owned)
-    exchange U, density  (3)      -> addBuoyancy (-1), vorticityConfinement (-3 / +3)
+    exchange U, density  (4)      -> addBuoyancy on owned +- 3 planes, vorticityConfinement (-3 / +3)
     exchange U, p        (5)      -> CNN projection: wall mask + sum/sumsq on owned planes,
                                      all-reduce of the two sums (the input scale), conv stack on the
                                      whole local slab, velocity update on owned planes
@@ -123,17 +123,32 @@ class SlabSimulator:
             t.applyBC(s["density"], s["densityBCInvMask"], s["densityBC"])
 
     def step(self):
+        """One tfluids.simulate on this rank's slab; communication through torch.distributed."""
+        for req in self.phases():
+            if req[0] == "halo":
+                self.dec.exchange(req[1], req[2], self.group)
+            elif self.world > 1:
+                dist.all_reduce(req[1], group=self.group)
+
+    def phases(self):
+        """The step as a generator that yields its communication requests -- ("halo", tensors,
+        width) or ("sum", tensor) -- so that a driver can satisfy them with torch.distributed
+        (`step`) or, in tests, between several slabs living in one process (`run_lockstep`)."""
         t, s, m, d = self.tfluids, self.s, self.mconf, self.dec
         p, U, flags, rho = s["pDiv"], s["UDiv"], s["flags"], s["density"]
         method, strength = m.get("advectionMethod"), m.get("maccormackStrength")
-        d.exchange([U, rho], d.halo, self.group)
+        yield ("halo", [U, rho], d.halo)
         self._slab_on()
         t.advectScalar(m["dt"], rho, U, flags, method, None, False, strength)
         t.advectVel(m["dt"], U, flags, method, None, strength)
         self._slab_off()
         self._bc()
-        d.exchange([U, rho], 3, self.group)
-        self._slab_on()
+        yield ("halo", [U, rho], 4)
+        # Buoyancy is point-wise in U but vorticity confinement then reads U three planes across the
+        # cut: apply the buoyancy on those ghost planes too (it needs density one plane further).
+        ext_lo = d.own_lo - min(3, d.lo_halo)
+        ext_hi = d.own_hi + min(3, d.hi_halo)
+        self.ctx.set_slab(d.zoff, d.gnz, ext_lo, ext_hi)
         dx = 1.0 / max(d.gnz, flags.size(3), flags.size(4))
         if m.get("buoyancyScale", 0) > 0:
             k = torch.tensor(-(dx / 4) * m["buoyancyScale"], dtype=torch.float32).item()
@@ -141,17 +156,20 @@ class SlabSimulator:
             gv = [torch.tensor(float(v), dtype=torch.float32).item() * k for v in g]
             gv = [torch.tensor(v, dtype=torch.float32).item() for v in gv]
             t.addBuoyancy(U, flags, rho, gv, m["dt"])
+        self._slab_on()
         if m.get("vorticityConfinementAmp", 0) > 0:
             t.vorticityConfinement(U, flags, dx * m["vorticityConfinementAmp"])
         self._slab_off()
         self._bc()
-        d.exchange([U, p], 5, self.group)
+        yield ("halo", [U, p], 5)
         self._slab_on()
         c, lib = self.ctx, self.ctx.lib
         c.use_current_stream()
         c.check(lib.tfl_cnn_stats(c.h, t._grid(U), t._grid(flags), t._grid(self.U1), C.c_void_p(self.sums.data_ptr())))
-        if self.world > 1:
-            dist.all_reduce(self.sums, group=self.group)
+        self._slab_off()
+        yield ("sum", self.sums)
+        self._slab_on()
+        c.use_current_stream()
         c.check(lib.tfl_cnn_project_from_sums(c.h, self.model.h, t._grid(p), t._grid(self.U1), t._grid(flags),
                                               C.c_void_p(self.sums.data_ptr()), t._grid(p), t._grid(U),
                                               float(self.model.threshold)))
@@ -185,3 +203,32 @@ class SlabSimulator:
             if r == self.rank:
                 parts[r].copy_(mine)
             dist.broadcast(parts[r], src=r, group=self.group)
+
+
+def run_lockstep(sims):
+    """Advance several SlabSimulators of ONE decomposition that live in the same process (tests:
+    the whole multi-rank logic on a single GPU).  Halo requests are served by direct copies between
+    neighbouring slabs, sum requests by adding the partial sums."""
+    sims = sorted(sims, key=lambda q: q.dec.rank)
+    gens = [q.phases() for q in sims]
+    while True:
+        reqs = []
+        for g in gens:
+            try:
+                reqs.append(next(g))
+            except StopIteration:
+                reqs.append(None)
+        if all(r is None for r in reqs):
+            return
+        assert all(r is not None for r in reqs) and len({r[0] for r in reqs}) == 1
+        if reqs[0][0] == "sum":
+            total = sum(r[1].clone() for r in reqs)
+            for r in reqs:
+                r[1].copy_(total)
+        else:
+            width = reqs[0][2]
+            for lo, hi in zip(range(len(sims) - 1), range(1, len(sims))):
+                a, b = sims[lo].dec, sims[hi].dec
+                for ta, tb in zip(reqs[lo][1], reqs[hi][1]):
+                    tb[:, :, b.own_lo - width:b.own_lo].copy_(ta[:, :, a.own_hi - width:a.own_hi])
+                    ta[:, :, a.own_hi:a.own_hi + width].copy_(tb[:, :, b.own_lo:b.own_lo + width])
