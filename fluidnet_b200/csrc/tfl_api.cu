@@ -30,6 +30,8 @@ struct tfl_ctx {
   bool slab = false;
   int zoff = 0, gnz = 0, zlo = 0, zhi = 0;
   int slab_margin = 2;                      // extra planes on which forward passes are evaluated
+  cudaStream_t side_stream = nullptr;       // density advection runs beside velocity advection
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct tfl_cnn {
@@ -190,6 +192,9 @@ int tfl_create(tfl_ctx** out, int device) {
   cudaMemset(c->counters, 0, 16 * sizeof(unsigned long long));
   if (cudaMalloc(&p, 256 * sizeof(double)) != cudaSuccess) { delete c; return 1; }
   c->dscratch = (double*)p;
+  cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   *out = c;
   return 0;
 }
@@ -201,6 +206,9 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->dscratch) cudaFree(ctx->dscratch);
+  if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -375,11 +383,12 @@ int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* f
   Geo g;
   if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
   const size_t cells = (size_t)g.n * g.nb;
-  if (arena_reserve(ctx, carve_bytes({cells * 3 * 4, cells * 4}))) return 1;
+  if (arena_reserve(ctx, carve_bytes({cells * 3 * 4, cells * 4, cells * 3 * 4}))) return 1;
   Carver cv(ctx);
   float* curl = cv.take<float>(cells * 3);
   float* cnorm = cv.take<float>(cells);
-  ctx->launches += launch_vorticity(U->data, flags->data, strength, curl, cnorm, g, ctx->stream);
+  float* force = cv.take<float>(cells * 3);
+  ctx->launches += launch_vorticity(U->data, flags->data, strength, curl, cnorm, force, g, ctx->stream);
   return check_launch(ctx, "vorticityConfinement");
 }
 
@@ -775,7 +784,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   const bool has_density = s->density.data != nullptr;
   if (cnn_ensure_act(ctx, m, g)) return 1;
   if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4, cells * 4 * g.nc, cells * 4 * g.nc,
-                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells})))
+                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells, cells * 12})))
     return 1;
   Carver cv(ctx);
   float* fwd_s = cv.take<float>(cells);
@@ -788,15 +797,21 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   float* p_net = cv.take<float>(cells);
   float* scale = cv.take<float>(g.nb);
   unsigned char* fl8 = cv.take<unsigned char>(cells);
+  float* force = cv.take<float>(cells * 3);
   cudaStream_t st = ctx->stream;
   // Byte copy of the flags for this step (every bit the kernels test is below 256).
   launch_flags_to_u8(s->flags.data, fl8, (long long)cells, st);
   ctx->launches += 1;
   if (has_density) {
+    // Density and velocity advection are independent (both read the old U): run the density
+    // kernels on a side stream so the two latency-bound kernel pairs overlap.
+    TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
     const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, mc->advection_method, 0,
-                                        mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, st);
+                                        mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
     if (nl < 0) return fail(ctx, "advectScalar: bad method");
     ctx->launches += nl;
+    TFL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
   }
   {
     const int nl = launch_advect_vel(mc->dt, s->U.data, fl8, mc->advection_method,
@@ -804,6 +819,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     if (nl < 0) return fail(ctx, "advectVel: bad method");
     ctx->launches += nl;
   }
+  if (has_density) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
   const int dmax = std::max(g.nx, std::max(g.ny, g.gnz));
   const double dx = 1.0 / (double)dmax;
   const bool u_bc = s->U_bc.data && s->U_bc_inv_mask.data;
@@ -830,12 +846,12 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   const int do_vort = mc->vorticity_confinement_amp > 0.0;
   const float amp = (float)(dx * mc->vorticity_confinement_amp);
   if (do_vort) {
-    launch_vort_curl(s->U.data, curl, cnorm, g, st);
-    ctx->launches += 1;
+    launch_vort_curl(s->U.data, curl, cnorm, force, amp, g, st);
+    ctx->launches += 2;
   }
   double* sums = ctx->dscratch + 64;
   TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
-  launch_vort_bc_mask(s->U.data, fl8, curl, cnorm, do_vort, amp, u_bc ? s->U_bc_inv_mask.data : nullptr,
+  launch_vort_bc_mask(s->U.data, fl8, force, do_vort, u_bc ? s->U_bc_inv_mask.data : nullptr,
                       u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
   const ConvTcGeo& tg = m->act_geo;
   const int split = m->mode == 2 ? 1 : 0;

@@ -75,8 +75,7 @@ __global__ void k_post_advect(const float* __restrict__ tmp_s, const float* __re
 // sums for the input scale.
 template <bool IS3D, typename FT>
 __global__ void k_vort_bc_mask(float* __restrict__ U, const FT* __restrict__ flags,
-                               const float* __restrict__ curl, const float* __restrict__ cnorm,
-                               int do_vort, float strength, BcPtrs bc, int mask_mode,
+                               const float* __restrict__ force, int do_vort, BcPtrs bc, int mask_mode,
                                double* __restrict__ sums, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
@@ -92,16 +91,15 @@ __global__ void k_vort_bc_mask(float* __restrict__ U, const FT* __restrict__ fla
       const int fc = flag_i(fl, g, k, j, i);
       const bool cf = fc & kFluid, ce = fc & kEmpty;
       if (cf || ce) {
-        const float* cb = curl + (long long)b * 3 * g.n;
-        const float* cn = cnorm + b * g.n;
-        const V3 f0 = conf_force(cb, cn, g, k, j, i, strength);
+        const float* fb = force + (long long)b * 3 * g.n;
         int f = flag_i(fl, g, k, j, i - 1);
-        if ((f & kFluid) || (cf && (f & kEmpty))) u[0] += (0.5f * (conf_force(cb, cn, g, k, j, i - 1, strength).x + f0.x));
+        if ((f & kFluid) || (cf && (f & kEmpty))) u[0] += (0.5f * (__ldg(fb + c - 1) + __ldg(fb + c)));
         f = flag_i(fl, g, k, j - 1, i);
-        if ((f & kFluid) || (cf && (f & kEmpty))) u[1] += (0.5f * (conf_force(cb, cn, g, k, j - 1, i, strength).y + f0.y));
+        if ((f & kFluid) || (cf && (f & kEmpty))) u[1] += (0.5f * (__ldg(fb + g.n + c - g.nx) + __ldg(fb + g.n + c)));
         if (g.is3d) {
           f = flag_i(fl, g, k - 1, j, i);
-          if ((f & kFluid) || (cf && (f & kEmpty))) u[2] += (0.5f * (conf_force(cb, cn, g, k - 1, j, i, strength).z + f0.z));
+          if ((f & kFluid) || (cf && (f & kEmpty)))
+            u[2] += (0.5f * (__ldg(fb + 2 * g.n + c - g.nx * g.ny) + __ldg(fb + 2 * g.n + c)));
         }
       }
     }
@@ -211,11 +209,11 @@ void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned c
   BcPtrs bc{u_inv, u_bc, d_inv, d_bc};
   TFL_LAUNCH3F(k_post_advect, g, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
 }
-void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* curl, const float* cnorm, int do_vort,
-                         float strength, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
+void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort,
+                         const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
-  TFL_LAUNCH3F(k_vort_bc_mask, g, st, U, flags, curl, cnorm, do_vort, strength, bc, mask_mode, sums, g);
+  TFL_LAUNCH3F(k_vort_bc_mask, g, st, U, flags, force, do_vort, bc, mask_mode, sums, g);
 }
 void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,

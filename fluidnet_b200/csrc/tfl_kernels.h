@@ -23,8 +23,8 @@ void launch_add_buoyancy(float* U, const FT* flags, const float* rho, const floa
 template <typename FT>
 void launch_add_gravity(float* U, const FT* flags, const float f[3], const Geo& g, cudaStream_t st);
 template <typename FT>
-int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, const Geo& g,
-                     cudaStream_t st);
+int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, float* force,
+                     const Geo& g, cudaStream_t st);
 // g: range of the result; g_fwd: (wider, in slab mode) range of the forward pass.
 template <typename FT>
 int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, int method,
@@ -58,9 +58,9 @@ void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, 
 void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
-void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st);
-void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* curl, const float* cnorm, int do_vort,
-                         float strength, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
+void launch_vort_curl(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
+                      cudaStream_t st);
+void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st);
 void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,

@@ -197,10 +197,22 @@ __global__ void k_vort_curl(const float* __restrict__ U, float* __restrict__ cur
   cnorm[b * g.n + c] = nrm;
 }
 
+// Confinement force per cell (zero on the border), third_party/tfluids.cc:1411-1439.
+template <bool IS3D, typename FT>
+__global__ void k_vort_force(const float* __restrict__ curl, const float* __restrict__ cnorm,
+                             float* __restrict__ force, float strength, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const V3 f = conf_force(curl + (long long)b * 3 * g.n, cnorm + b * g.n, g, k, j, i, strength);
+  float* fb = force + (long long)b * 3 * g.n + cell(g, k, j, i);
+  fb[0] = f.x; fb[g.n] = f.y; fb[2 * g.n] = f.z;
+}
+
+// AddForceField, third_party/tfluids.cc:1312-1339 (CPU caller guards the border, :1443-1451).
 template <bool IS3D, typename FT>
 __global__ void k_vort_apply(float* __restrict__ U, const FT* __restrict__ flags,
-                             const float* __restrict__ curl, const float* __restrict__ cnorm,
-                             float strength, Geo gin) {
+                             const float* __restrict__ force, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
@@ -209,21 +221,18 @@ __global__ void k_vort_apply(float* __restrict__ U, const FT* __restrict__ flags
   const int fc = flag_i(fl, g, k, j, i);
   const bool cf = fc & kFluid, ce = fc & kEmpty;
   if (!cf && !ce) return;
-  const float* cb = curl + (long long)b * 3 * g.n;
-  const float* cn = cnorm + b * g.n;
+  const float* fb = force + (long long)b * 3 * g.n;
   float* ub = U + (long long)b * g.nc * g.n;
   const int c = cell(g, k, j, i);
-  const V3 f0 = conf_force(cb, cn, g, k, j, i, strength);
   int f = flag_i(fl, g, k, j, i - 1);
-  if ((f & kFluid) || (cf && (f & kEmpty)))
-    ub[c] += (0.5f * (conf_force(cb, cn, g, k, j, i - 1, strength).x + f0.x));
+  if ((f & kFluid) || (cf && (f & kEmpty))) ub[c] += (0.5f * (__ldg(fb + c - 1) + __ldg(fb + c)));
   f = flag_i(fl, g, k, j - 1, i);
   if ((f & kFluid) || (cf && (f & kEmpty)))
-    ub[g.n + c] += (0.5f * (conf_force(cb, cn, g, k, j - 1, i, strength).y + f0.y));
+    ub[g.n + c] += (0.5f * (__ldg(fb + g.n + c - g.nx) + __ldg(fb + g.n + c)));
   if (g.is3d) {
     f = flag_i(fl, g, k - 1, j, i);
     if ((f & kFluid) || (cf && (f & kEmpty)))
-      ub[2 * g.n + c] += (0.5f * (conf_force(cb, cn, g, k - 1, j, i, strength).z + f0.z));
+      ub[2 * g.n + c] += (0.5f * (__ldg(fb + 2 * g.n + c - g.nx * g.ny) + __ldg(fb + 2 * g.n + c)));
   }
 }
 
@@ -744,23 +753,24 @@ template <typename FT>
 void launch_add_gravity(float* U, const FT* flags, const float f[3], const Geo& g, cudaStream_t st) {
   TFL_LAUNCH3(k_add_gravity, FT, g, st, U, flags, f[0], f[1], f[2], g);
 }
-void launch_vort_curl(const float* U, float* curl, float* cnorm, const Geo& g, cudaStream_t st) {
+// curl + |curl| on [zlo-2, zhi+1), then the force on [zlo-1, zhi) (what AddForceField on
+// [zlo, zhi) reads).  force always has 3 channels.
+void launch_vort_curl(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
+                      cudaStream_t st) {
   Geo g1 = g;
   g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
   g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
   TFL_LAUNCH3(k_vort_curl, float, g1, st, U, curl, cnorm, g1);
+  Geo g2 = g;
+  g2.zlo = g.zlo - 1 < 0 ? 0 : g.zlo - 1;
+  TFL_LAUNCH3(k_vort_force, float, g2, st, curl, cnorm, force, strength, g2);
 }
 template <typename FT>
-int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, const Geo& g,
-                     cudaStream_t st) {
-  // curl / |curl| are needed one cell beyond the computed range in every direction
-  // (confinement force at i-1 reads |curl| at i-2): widen the first pass in z.
-  Geo g1 = g;
-  g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
-  g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;
-  TFL_LAUNCH3(k_vort_curl, FT, g1, st, U, curl, cnorm, g1);
-  TFL_LAUNCH3(k_vort_apply, FT, g, st, U, flags, curl, cnorm, strength, g);
-  return 2;
+int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, float* force,
+                     const Geo& g, cudaStream_t st) {
+  launch_vort_curl(U, curl, cnorm, force, strength, g, st);
+  TFL_LAUNCH3(k_vort_apply, FT, g, st, U, flags, force, g);
+  return 3;
 }
 
 template <typename FT>
@@ -857,7 +867,7 @@ void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st) {
   template void launch_velocity_update<FT>(float*, const FT*, const float*, const Geo&, cudaStream_t);       \
   template void launch_add_buoyancy<FT>(float*, const FT*, const float*, const float*, const Geo&, cudaStream_t); \
   template void launch_add_gravity<FT>(float*, const FT*, const float*, const Geo&, cudaStream_t);           \
-  template int launch_vorticity<FT>(float*, const FT*, float, float*, float*, const Geo&, cudaStream_t);     \
+  template int launch_vorticity<FT>(float*, const FT*, float, float*, float*, float*, const Geo&, cudaStream_t); \
   template int launch_advect_scalar<FT>(float, const float*, const float*, const FT*, int, int, float, float*, \
                                         float*, float*, const Geo&, const Geo&, cudaStream_t);               \
   template int launch_advect_vel<FT>(float, const float*, const FT*, int, float, float*, float*, const Geo&,  \
