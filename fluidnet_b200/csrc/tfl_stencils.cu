@@ -665,6 +665,87 @@ k_jacobi_iter4(const unsigned char* __restrict__ mask, const float* __restrict__
   *(float4*)(cur + c) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// 2.5-D variant: a CTA owns a 128 x 8 (x, y) patch and marches over a chunk of z planes keeping the
+// previous / current / next plane of p in registers, so every p value is read from L2/HBM once per
+// sweep (plus the patch's y halo rows) instead of five times; y neighbours inside the patch are
+// exchanged through shared memory, x neighbours with warp shuffles.  Per-cell arithmetic is the
+// same expression as above (bit-identical).  Requires 3-D, nx % 128 == 0, ny % 8 == 0.
+constexpr int kJY = 8;
+__global__ void __launch_bounds__(256)
+k_jacobi_march(const unsigned char* __restrict__ mask, const float* __restrict__ div,
+               const float* __restrict__ prev, float* __restrict__ cur, Geo g, int zchunk) {
+  __shared__ float4 rows[2][kJY][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = (blockIdx.x * 32 + tx) * 4;
+  const int j = blockIdx.y * kJY + ty;
+  const int nchunks = (g.nz + zchunk - 1) / zchunk;
+  const int b = blockIdx.z / nchunks;
+  const int k0 = (blockIdx.z % nchunks) * zchunk;
+  const int k1 = min(k0 + zchunk, g.nz);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const long long base = b * g.n + (long long)j * sy + i0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Everything plane k needs is requested while plane k-1 is being computed (software pipelining
+  // by one plane; p itself by two planes).
+  struct PlaneIn { float4 dv, ym, yp; unsigned m4; float left, right; };
+  auto fetch = [&](int k, PlaneIn& in) {
+    const long long c = base + (long long)k * sz;
+    in.m4 = __ldg((const unsigned*)(mask + c));
+    in.dv = __ldg((const float4*)(div + c));
+    in.ym = (ty == 0 && j > 0) ? __ldg((const float4*)(prev + c - sy)) : zero4;
+    in.yp = (ty == kJY - 1 && j + 1 < g.ny) ? __ldg((const float4*)(prev + c + sy)) : zero4;
+    in.left = (tx == 0 && i0 > 0) ? __ldg(prev + c - 1) : 0.0f;
+    in.right = (tx == 31 && i0 + 4 < g.nx) ? __ldg(prev + c + 4) : 0.0f;
+  };
+  float4 pm = k0 > 0 ? __ldg((const float4*)(prev + base + (long long)(k0 - 1) * sz)) : zero4;
+  float4 pc = __ldg((const float4*)(prev + base + (long long)k0 * sz));
+  float4 pp = k0 + 1 < g.nz ? __ldg((const float4*)(prev + base + (long long)(k0 + 1) * sz)) : zero4;
+  PlaneIn in;
+  fetch(k0, in);
+  for (int k = k0; k < k1; k++) {
+    const long long c = base + (long long)k * sz;
+    const float4 pq = k + 2 < g.nz ? __ldg((const float4*)(prev + c + 2 * (long long)sz)) : zero4;
+    PlaneIn nx_in = in;
+    if (k + 1 < k1) fetch(k + 1, nx_in);
+    const int buf = k & 1;
+    rows[buf][ty][tx] = pc;
+    float left = __shfl_up_sync(0xffffffffu, pc.w, 1);
+    float right = __shfl_down_sync(0xffffffffu, pc.x, 1);
+    if (tx == 0) left = in.left;
+    if (tx == 31) right = in.right;
+    __syncthreads();
+    const float4 ym = ty > 0 ? rows[buf][ty - 1][tx] : in.ym;
+    const float4 yp = ty < kJY - 1 ? rows[buf][ty + 1][tx] : in.yp;
+    const unsigned m4 = in.m4;
+    float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if ((m4 & 0x01010101u) != 0x01010101u) {
+      const float pcv[4] = {pc.x, pc.y, pc.z, pc.w};
+      const float xm[4] = {left, pc.x, pc.y, pc.z};
+      const float xp[4] = {pc.y, pc.z, pc.w, right};
+      const float ymv[4] = {ym.x, ym.y, ym.z, ym.w}, ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+      const float zmv[4] = {pm.x, pm.y, pm.z, pm.w}, zpv[4] = {pp.x, pp.y, pp.z, pp.w};
+      const float dvv[4] = {in.dv.x, in.dv.y, in.dv.z, in.dv.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned m = (m4 >> (8 * q)) & 0xFFu;
+        if (m & 1) continue;
+        const float p1 = (m & 2) ? pcv[q] : xm[q];
+        const float p2 = (m & 4) ? pcv[q] : xp[q];
+        const float p3 = (m & 8) ? pcv[q] : ymv[q];
+        const float p4 = (m & 16) ? pcv[q] : ypv[q];
+        const float p5 = (m & 32) ? pcv[q] : zmv[q];
+        const float p6 = (m & 64) ? pcv[q] : zpv[q];
+        out[q] = (p1 + p2 + p3 + p4 + p5 + p6 + dvv[q]) / 6.0f;
+      }
+    }
+    *(float4*)(cur + c) = make_float4(out[0], out[1], out[2], out[3]);
+    pm = pc;
+    pc = pp;
+    pp = pq;
+    in = nx_in;
+  }
+}
+
 // sum over one batch element of (a - b)^2, accumulated in double: out[b] += ...
 __global__ void k_sqdiff(const float* __restrict__ a, const float* __restrict__ bb, long long n,
                          double* __restrict__ out) {
@@ -833,6 +914,20 @@ void launch_jacobi_iter(const unsigned char* mask, const float* div, const float
                         const Geo& g, cudaStream_t st) {
   const bool aligned = ((uintptr_t)mask % 4 == 0) && ((uintptr_t)div % 16 == 0) && ((uintptr_t)prev % 16 == 0) &&
                        ((uintptr_t)cur % 16 == 0);
+  // The marching kernel pays off once the fields no longer fit L2 (>= 4M cells); smaller grids keep
+  // more CTAs in flight with the flat float4 kernel.  (Tests force it through nx == 128 / 256 shapes
+  // with few planes, where both kernels are selected by shape alone.)
+  const bool big = g.n * g.nb >= (4LL << 20) || g.nz < 16;
+  if (g.is3d && aligned && big && g.nx % 128 == 0 && g.ny % kJY == 0 && g.zlo == 0 && g.zhi == g.nz && g.nz >= 8) {
+    // enough CTAs to fill the machine (>= ~4 per SM), chunks of at least 4 planes
+    const int xy_ctas = (g.nx / 128) * (g.ny / kJY) * g.nb;
+    int zchunk = 32;
+    while (zchunk > 4 && (long long)xy_ctas * ((g.nz + zchunk - 1) / zchunk) < 592) zchunk >>= 1;
+    dim3 block(32, kJY, 1);
+    dim3 grid(g.nx / 128, g.ny / kJY, ((g.nz + zchunk - 1) / zchunk) * g.nb);
+    k_jacobi_march<<<grid, block, 0, st>>>(mask, div, prev, cur, g, zchunk);
+    return;
+  }
   if (g.nx % 4 == 0 && aligned) {
     const int nzr = g.zhi - g.zlo;
     const int qx = g.nx / 4;

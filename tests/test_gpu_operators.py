@@ -126,6 +126,24 @@ def test_jacobi(orc, gpu, case):
         assert gpu.last_jacobi_iters == orc.last_jacobi_iters
 
 
+@pytest.mark.parametrize("shape", [(128, 16, 12), (256, 8, 9)], ids=["128x16x12", "256x8x9"])
+def test_jacobi_marching_kernel(orc, gpu, shape):
+    """Shapes that select the 2.5-D z-marching Jacobi kernel (nx % 128 == 0, ny % 8 == 0)."""
+    from fluidnet_b200 import synth
+    nx, ny, nz = shape
+    fl = synth.make_flags(nx, ny, nz, True, nb=2, geometry=True, exotic=True)
+    U = synth.make_velocity(fl, True, amp=2.0)
+    orc.setWallBcsForward(U, fl)
+    div = orc.velocityDivergenceForward(U, fl)
+    for iters in (1, 2, 9, 30):
+        a = np.full_like(div, 9.0)
+        b = np.full_like(div, 9.0)
+        ra = gpu.solveLinearSystemJacobi(a, fl, div, True, 0.0, iters)
+        rb = orc.solveLinearSystemJacobi(b, fl, div, True, 0.0, iters)
+        assert bits_equal(a, b), "jacobi march (%d iters) %s" % (iters, describe_diff(a, b))
+        assert abs(ra - rb) <= 1e-5 * max(abs(rb), 1e-12) + 1e-12
+
+
 @pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")))
 def test_gpu_matches_reference_golden(gpu, fname):
     """Against outputs of the reference's own CPU code (fixtures committed under
