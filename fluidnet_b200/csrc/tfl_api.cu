@@ -45,6 +45,8 @@ struct tfl_cnn {
   int mode = 0;              // 0 fp32 FMA, 1 TF32 tensor cores, 2 3xTF32 tensor cores
   bool tc_ok = false;
   float* wB[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [split][layer]
+  float* wTS[3] = {nullptr, nullptr, nullptr};   // weight blocks of the TMEM-operand kernel
+  int use_ts = 1;            // mode 2 prefers the TMEM-operand kernel where it applies
   float* tail = nullptr;     // w4[8][8], b4[8], w5[8], b5[1]
   float* act[3] = {nullptr, nullptr, nullptr};   // padded channels-last activation buffers
   ConvTcGeo act_geo = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -574,6 +576,12 @@ int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, co
         cudaMalloc((void**)&m->wB[split][l], packed.size() * 4);
         cudaMemcpy(m->wB[split][l], packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
       }
+    for (int l = 0; l < 3; l++) {
+      std::vector<float> packed(conv_ts_b_floats());
+      conv_ts_pack_weights(weights[l], cin[l], packed.data());
+      cudaMalloc((void**)&m->wTS[l], packed.size() * 4);
+      cudaMemcpy(m->wTS[l], packed.data(), packed.size() * 4, cudaMemcpyHostToDevice);
+    }
     std::vector<float> tail(64 + 8 + 8 + 1);
     memcpy(tail.data(), weights[3], 64 * 4);
     memcpy(tail.data() + 64, biases[3], 8 * 4);
@@ -595,8 +603,12 @@ int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
   return 0;
 }
 int tfl_cnn_get_mode(const tfl_cnn* m) { return m ? m->mode : -1; }
+// Undocumented debugging hook: 0 forces the shared-memory-operand kernel in 3xTF32 mode.
+int tfl_debug_cnn_use_ts(tfl_cnn* m, int on) { if (m) m->use_ts = on; return 0; }
 // Undocumented debugging hook (not in tfl.h): per-CTA phase timestamps of the tensor-core conv.
 int tfl_debug_conv_timestamps(void* dev_buf) { conv_tc_set_debug((long long*)dev_buf); return 0; }
+int tfl_debug_conv_ts_counters(void* dev_buf) { conv_ts_set_debug((long long*)dev_buf); return 0; }
+int tfl_debug_conv_ts_variant(int v) { conv_ts_set_variant(v); return 0; }
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   if (!m) return;
@@ -607,6 +619,8 @@ void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
     for (int l = 0; l < 3; l++)
       if (m->wB[sp][l]) cudaFree(m->wB[sp][l]);
   if (m->tail) cudaFree(m->tail);
+  for (float* p : m->wTS)
+    if (p) cudaFree(p);
   for (float* p : m->act)
     if (p) cudaFree(p);
   delete m;
@@ -625,6 +639,21 @@ static int cnn_ensure_act(tfl_ctx* ctx, tfl_cnn* m, const Geo& g) {
     TFL_CUDA(ctx, cudaMemset(m->act[i], 0, conv_tc_act_bytes(m->act_geo)));
   }
   return 0;
+}
+
+// The three 3x3x3 layers (+ fused 1x1x1 tail) on tensor cores: act[0] -> act[1] -> act[2] -> p_net.
+static void run_conv_stack(tfl_cnn* m, float* p_net, cudaStream_t st) {
+  const ConvTcGeo& tg = m->act_geo;
+  if (m->mode == 2 && m->use_ts && conv_ts_supported(tg)) {
+    launch_conv3_ts(m->act[0], m->act[1], nullptr, m->wTS[0], m->b[0], nullptr, 1, 0, tg, st);
+    launch_conv3_ts(m->act[1], m->act[2], nullptr, m->wTS[1], m->b[1], nullptr, 2, 0, tg, st);
+    launch_conv3_ts(m->act[2], nullptr, p_net, m->wTS[2], m->b[2], m->tail, 2, 1, tg, st);
+    return;
+  }
+  const int split = m->mode == 2 ? 1 : 0;
+  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
+  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
+  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
 }
 
 static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const float* U_div,
@@ -647,12 +676,9 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   if (m->mode > 0 && m->tc_ok && !ctx->slab) {
     if (cnn_ensure_act(ctx, m, g)) return 1;
     const ConvTcGeo& tg = m->act_geo;
-    const int split = m->mode == 2 ? 1 : 0;
     launch_cnn_inputs_padded(p_div, U1, flags, scale, m->act[0], tg.px, tg.py, g, st);
-    launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
-    launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
     float* p_net = actA;      // plain [b][z][y][x]
-    launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+    run_conv_stack(m, p_net, st);
     launch_cnn_finish(p_net, U1, flags, scale, p_out, U_out, g, st);
     ctx->launches += 7;
     if (scale_dev_out) *scale_dev_out = scale;
@@ -755,11 +781,8 @@ int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, c
     gi.zhi = (g.zoff + g.nz == g.gnz) ? g.nz : g.nz - 2;
   }
   const ConvTcGeo& tg = m->act_geo;
-  const int split = m->mode == 2 ? 1 : 0;
   launch_cnn_inputs_padded(p_div->data, U1->data, flags->data, scale, m->act[0], tg.px, tg.py, gi, st);
-  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
-  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
-  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+  run_conv_stack(m, p_net, st);
   launch_cnn_finish(p_net, U1->data, flags->data, scale, p_out->data, U_out->data, g, st);
   ctx->launches += 6;
   return check_launch(ctx, "cnn_project_from_sums");
@@ -854,12 +877,9 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   launch_vort_bc_mask(s->U.data, fl8, force, do_vort, u_bc ? s->U_bc_inv_mask.data : nullptr,
                       u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
   const ConvTcGeo& tg = m->act_geo;
-  const int split = m->mode == 2 ? 1 : 0;
   launch_cnn_inputs_fused(s->p.data, s->U.data, fl8, sums, mc->normalize_input_threshold, scale, m->act[0],
                           tg.px, tg.py, g, st);
-  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
-  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
-  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+  run_conv_stack(m, p_net, st);
   launch_cnn_finish_fused(p_net, s->U.data, fl8, scale, s->p.data, u_bc ? s->U_bc_inv_mask.data : nullptr,
                           u_bc ? s->U_bc.data : nullptr, -1e6f, 1e6f, g, st);
   ctx->launches += 6;
