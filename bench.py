@@ -398,7 +398,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "advectVel (k_advect_vel_pass1+pass2, maccormackOurs)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms},
+                     "traffic": 84.9e6 if n == 128 else None,   # ncu dram read+write, both passes (profiles/r01_ncu_summary.md)
+                     "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms},
         "roofline_extra": extra,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
