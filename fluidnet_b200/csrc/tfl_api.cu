@@ -32,6 +32,7 @@ struct tfl_ctx {
   int slab_margin = 2;                      // extra planes on which forward passes are evaluated
   cudaStream_t side_stream = nullptr;       // density advection runs beside velocity advection
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  PcgScratch pcg;                           // grow-only buffers of the PCG solve
 };
 
 struct tfl_cnn {
@@ -208,6 +209,7 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->dscratch) cudaFree(ctx->dscratch);
+  pcg_release(ctx->pcg);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -512,6 +514,33 @@ int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_gr
   if (residual) *residual = res;
   if (iterations) *iterations = iter;
   return 0;
+}
+
+int tfl_precond_from_string(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "none")) return TFL_PRECOND_NONE;
+  if (!strcmp(name, "ilu0")) return TFL_PRECOND_ILU0;
+  if (!strcmp(name, "ic0")) return TFL_PRECOND_IC0;
+  return -1;
+}
+
+int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, const tfl_grid* div,
+                                int is_3d, int precond, float tol, int max_iter, float* residual,
+                                int* iterations) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
+  if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
+  if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
+  if (precond < TFL_PRECOND_NONE || precond > TFL_PRECOND_IC0)
+    return fail(ctx, "Incorrect preconType ('none', 'ic0', 'ilu0')");      // generic/tfluids.cu:1551
+  if (ctx->slab) return fail(ctx, "PCG does not shard (triangular solves): single GPU only");
+  if ((long long)flags->nb * flags->nz * flags->ny * flags->nx >= (1ll << 31)) return fail(ctx, "PCG: grid too large");
+  if (arena_reserve(ctx, pcg_workspace_bytes(flags->nb, flags->nz, flags->ny, flags->nx))) return 1;
+  const int rc = pcg_solve(ctx->pcg, ctx->arena, p->data, flags->data, div->data, flags->nb, flags->nz, flags->ny,
+                           flags->nx, is_3d, precond, tol, max_iter, residual, iterations, &ctx->launches,
+                           ctx->stream);
+  if (rc == 3) { cudaError_t e = cudaGetLastError(); return fail(ctx, "solveLinearSystemPCG: %s", cudaGetErrorString(e)); }
+  if (rc) return fail(ctx, "%s", pcg_status_string(rc));
+  return check_launch(ctx, "solveLinearSystemPCG");
 }
 
 int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc) {
@@ -935,6 +964,14 @@ int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl
     if (tfl_velocity_divergence_forward(ctx, &s->U, &s->flags, &s->div)) return 1;
     const int iters = mc->max_iter > 0 ? mc->max_iter : 100;
     if (tfl_solve_linear_system_jacobi(ctx, &s->p, &s->flags, &s->div, is3d, 0.0f, iters, nullptr, nullptr))
+      return 1;
+    if (tfl_velocity_update_forward(ctx, &s->U, &s->flags, &s->p)) return 1;
+  } else if (mc->sim_method == TFL_SIM_PCG) {                         // :280-286: tol 1e-4, 'ic0'
+    if (!s->div.data) return fail(ctx, "simulate: state.div scratch is required for jacobi/pcg");
+    if (tfl_velocity_divergence_forward(ctx, &s->U, &s->flags, &s->div)) return 1;
+    const int iters = mc->max_iter > 0 ? mc->max_iter : 100;
+    if (tfl_solve_linear_system_pcg(ctx, &s->p, &s->flags, &s->div, is3d, TFL_PRECOND_IC0, 1e-4f, iters, nullptr,
+                                    nullptr))
       return 1;
     if (tfl_velocity_update_forward(ctx, &s->U, &s->flags, &s->p)) return 1;
   } else {

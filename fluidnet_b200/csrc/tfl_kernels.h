@@ -75,4 +75,22 @@ void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* 
 int launch_conv_direct(const float* in, float* out, const float* wdev, const float* bdev, int cin, int cout,
                        int ksize, int relu, const Geo& g, cudaStream_t st);
 
+// ---- tfl_pcg.cu: matrix-free PCG pressure solve ----
+struct PcgScratch {            // owned by the context, grow-only
+  void* comp_buf = nullptr;    // per-component CG scalars
+  size_t comp_cap = 0;
+  unsigned long long* prog = nullptr;   // progress words of the triangular-sweep pipeline
+  size_t prog_cap = 0;
+  unsigned long long epoch = 0;
+  int* host = nullptr;         // pinned read-back words
+  int sm_count = 0;
+};
+size_t pcg_workspace_bytes(int nb, int nz, int ny, int nx);
+const char* pcg_status_string(int rc);
+// precond: 0 none, 1 ilu0, 2 ic0.  Returns 0 or a status for pcg_status_string.  Synchronises `st`.
+int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, const float* div, int nb, int nz, int ny,
+              int nx, int is3d, int precond, float tol, int max_iter, float* residual, int* iterations,
+              long long* launches, cudaStream_t st);
+void pcg_release(PcgScratch& sc);
+
 }  // namespace tfl

@@ -51,6 +51,9 @@ int tfl_add_gravity(tfl_ctx*, const tfl_grid* U, const tfl_grid* flags, const fl
 int tfl_vorticity_confinement(tfl_ctx*, const tfl_grid* U, const tfl_grid* flags, float strength);
 int tfl_solve_linear_system_jacobi(tfl_ctx*, const tfl_grid* p, const tfl_grid* flags, const tfl_grid* div,
                                    int is_3d, float p_tol, int max_iter, float* residual, int* iterations);
+int tfl_precond_from_string(const char* name);
+int tfl_solve_linear_system_pcg(tfl_ctx*, const tfl_grid* p, const tfl_grid* flags, const tfl_grid* div,
+                                int is_3d, int precond, float tol, int max_iter, float* residual, int* iterations);
 int tfl_empty_domain(tfl_ctx*, const tfl_grid* flags, int is_3d, int bnd);
 int tfl_flags_to_occupancy(tfl_ctx*, const tfl_grid* flags, const tfl_grid* occupancy, int64_t* bad_cells);
 int tfl_apply_bc(tfl_ctx*, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc);
@@ -193,6 +196,17 @@ function tfluids.solveLinearSystemJacobi(p, flags, div, is3D, pTol, maxIter, ver
   maxIter = maxIter or 1000
   local res = ffi.new('float[1]')
   check(lib.tfl_solve_linear_system_jacobi(ctx, p.c, flags.c, div.c, is3D and 1 or 0, pTol, maxIter, res, nil))
+  return res[0]
+end
+
+function tfluids.solveLinearSystemPCG(p, flags, div, is3D, tol, maxIter, precondType, verbose)
+  precondType = precondType or 'ic0'                                       -- init.lua:661-666
+  tol = tol or 1e-6
+  maxIter = maxIter or 1000
+  local kind = lib.tfl_precond_from_string(precondType)
+  if kind < 0 then error("Incorrect preconType ('none', 'ic0', 'ilu0')") end
+  local res = ffi.new('float[1]')
+  check(lib.tfl_solve_linear_system_pcg(ctx, p.c, flags.c, div.c, is3D and 1 or 0, kind, tol, maxIter, res, nil))
   return res[0]
 end
 

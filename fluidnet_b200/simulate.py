@@ -124,6 +124,9 @@ def simulate(conf, mconf, batch, model=None, outputDiv=False):
         if simMethod == "jacobi":
             tfluids.solveLinearSystemJacobi(p, flags, batch["div"], mconf["is3D"], 0,
                                             mconf.get("maxIter") or 100)
+        elif simMethod == "pcg":
+            tfluids.solveLinearSystemPCG(p, flags, batch["div"], mconf["is3D"], 1e-4,
+                                         mconf.get("maxIter") or 100, "ic0")
         else:
             raise ValueError("mconf.simMethod (%s) is not a valid option" % simMethod)
         tfluids.velocityUpdateForward(U, flags, p)

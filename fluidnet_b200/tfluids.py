@@ -274,6 +274,31 @@ def solveLinearSystemJacobi(p, flags, div, is3D, pTol=None, maxIter=None, verbos
     return float(res.value)
 
 
+def solveLinearSystemPCG(p, flags, div, is3D, tol=None, maxIter=None, precondType=None, verbose=None):
+    """init.lua:645-676 (same argument order and defaults). Returns the max residual across the
+    batch elements and connected fluid components."""
+    assert p.dim() == 5 and flags.dim() == 5 and div.dim() == 5, 'Dimension mismatch'
+    assert flags.size(1) == 1, 'flags is not scalar'
+    assert p.size() == flags.size(), 'size mismatch'
+    assert div.size() == flags.size(), 'size mismatch'
+    if not is3D:
+        assert flags.size(2) == 1, 'd > 1 for a 2D domain'
+    precondType = precondType or 'ic0'
+    tol = 1e-6 if tol is None else tol
+    maxIter = 1000 if maxIter is None else maxIter
+    assert p.is_contiguous() and flags.is_contiguous() and div.is_contiguous()
+    c = _ctx_for(p)
+    kind = c.lib.tfl_precond_from_string(precondType.encode())
+    if kind < 0:
+        raise TflError("Incorrect preconType ('none', 'ic0', 'ilu0')")
+    res = C.c_float(0)
+    it = C.c_int(0)
+    c.check(c.lib.tfl_solve_linear_system_pcg(c.h, _grid(p), _grid(flags), _grid(div), 1 if is3D else 0, kind,
+                                              float(tol), int(maxIter), C.byref(res), C.byref(it)))
+    solveLinearSystemPCG.last_iterations = it.value
+    return float(res.value)
+
+
 def applyBC(x, invMask, bc):
     """x:cmul(invMask); x:add(bc) -- the cutorch pair in setConstVals (lib/simulate.lua:136-158)."""
     c = _ctx_for(x)

@@ -127,6 +127,21 @@ int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* f
 int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
                                    const tfl_grid* div, int is_3d, float p_tol, int max_iter,
                                    float* residual, int* iterations);
+
+/* tfluids.solveLinearSystemPCG (init.lua:645-676; generic/tfluids.cu:1245-1759, CUDA only in the
+ * reference: host flood fill + CSR assembly, cuSPARSE ic0/ilu0 + csrsv + csrmv, cuBLAS dots).
+ * Here matrix-free and device-resident: p <- 0, then per connected component of fluid cells
+ * (components of one cell skipped, fewer than 5 cells un-preconditioned) Golub & Van Loan PCG with
+ * x0 = 0 until ||r||^2 <= tol^2 or iter > max_iter, the component's mean removed from the result.
+ * precond: TFL_PRECOND_NONE / ILU0 / IC0 (for the symmetric 7-point matrix ILU0 and IC0 are the
+ * same operator and share one factor).  *residual = max over components of ||r||_2 (-inf when no
+ * component was solved, as the reference), *iterations = the longest component's count.
+ * Errors like the reference: a fluid cell on the domain border, a NaN residual. */
+enum { TFL_PRECOND_NONE = 0, TFL_PRECOND_ILU0 = 1, TFL_PRECOND_IC0 = 2 };
+int tfl_precond_from_string(const char* name);   /* "none" | "ilu0" | "ic0"; -1 if unknown */
+int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
+                                const tfl_grid* div, int is_3d, int precond, float tol, int max_iter,
+                                float* residual, int* iterations);
 /* tfluids.emptyDomain (init.lua:545-555; generic/tfluids.cu:314-353). */
 int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd);
 /* tfluids.flagsToOccupancy (init.lua:571-576; generic/tfluids.cu:355-401).  Cells that are

@@ -191,6 +191,31 @@ class Oracle:
         self.last_jacobi_iters = it.value
         return float(res)
 
+    PRECOND = {"none": 0, "ilu0": 1, "ic0": 2}
+
+    def solveLinearSystemPCG(self, p, flags, div, is3D, tol=1e-6, maxIter=1000, precondType="ic0"):
+        """tfluids.solveLinearSystemPCG (tfluids/init.lua:645-676); returns the max residual."""
+        assert p.dtype == np.float32 and p.flags.c_contiguous
+        flags, div = _f32(flags), _f32(div)
+        d = _dims(flags, is3D)
+        res, it = C.c_float(0), C.c_int(0)
+        rc = self.lib.orc_pcg(_ptr(p), _ptr(flags), _ptr(div), C.byref(d), C.c_int(self.PRECOND[precondType]),
+                              C.c_float(tol), C.c_int(maxIter), C.byref(res), C.byref(it))
+        if rc:
+            raise RuntimeError("Non fluid cell found in a connected component")
+        self.last_pcg_iters = it.value
+        return float(res.value)
+
+    def findConnectedFluidComponents(self, flags, is3D, ibatch=0):
+        """(components [z][y][x] int32, sizes) of one batch element."""
+        flags = _f32(flags)
+        d = _dims(flags, is3D)
+        comp = np.empty(flags.shape[2:], np.int32)
+        sizes = np.zeros(comp.size + 1, np.int32)
+        n = self.lib.orc_find_components(_ptr(flags), C.byref(d), C.c_int(ibatch), _ptr(comp), _ptr(sizes),
+                                         C.c_int(sizes.size))
+        return comp, sizes[:n].copy()
+
     def calcLineTrace(self, pos, delta, flags, is3D=True):
         flags = _f32(flags)
         d = _dims(flags, is3D)
@@ -371,6 +396,20 @@ class Reference(Oracle):
         return bool(hit), out
 
 
+    def findConnectedFluidComponents(self, flags, is3D, ibatch=0):
+        flags = _f32(flags).copy()
+        comp = np.empty(flags.shape[2:], np.int32)
+        sizes = np.zeros(comp.size + 1, np.int32)
+        err = C.create_string_buffer(1024)
+        n = self.ref.ref_find_connected_fluid_components(
+            _ptr(flags), C.c_int(flags.shape[0]), C.c_int(flags.shape[2]), C.c_int(flags.shape[3]),
+            C.c_int(flags.shape[4]), C.c_int(1 if is3D else 0), C.c_int(ibatch), _ptr(comp), _ptr(sizes),
+            C.c_int(sizes.size), err, C.c_int(1024))
+        if n < 0:
+            raise RuntimeError("reference findConnectedFluidComponents: " + err.value.decode())
+        return comp, sizes[:n].copy()
+
+
 # ----------------------------------------------------------------------------------------
 # The loop around the operators (torch/lib/simulate.lua) and the projection model
 # (torch/lib/model.lua), restated on top of a backend (Oracle or Reference).
@@ -500,6 +539,8 @@ def simulate(be, mconf, batch, model=None):
         if mconf["simMethod"] == "jacobi":
             be.solveLinearSystemJacobi(p, flags, div, mconf["is3D"], 0.0,
                                        mconf.get("maxIter") or 100)
+        elif mconf["simMethod"] == "pcg":                       # lib/simulate.lua:280-286
+            be.solveLinearSystemPCG(p, flags, div, mconf["is3D"], 1e-4, mconf.get("maxIter") or 100, "ic0")
         else:
             raise ValueError("oracle simulate: simMethod %r not available on CPU"
                              % mconf["simMethod"])

@@ -174,6 +174,36 @@ int ref_calc_line_trace(const float* pos, const float* delta, float* flags,
   }
 }
 
+
+// The reference's connected-component labelling of fluid cells (CPU code used by its CUDA PCG,
+// torch/tfluids/generic/find_connected_fluid_components.cc:17-82).  flags is [nb][1][z][y][x];
+// components is [z][y][x] int32 for batch `ibatch`.  Returns the component count, sizes[] filled
+// up to max_sizes, -1 on a reference hard error.
+int ref_find_connected_fluid_components(float* flags, int nbatch, int zsize, int ysize, int xsize, int is_3d,
+                                        int ibatch, int* components, int* sizes, int max_sizes,
+                                        char* err, int errlen) {
+  THFloatTensor tf;
+  memset(&tf, 0, sizeof(tf));
+  long sz[5] = {nbatch, 1, zsize, ysize, xsize};
+  tf.data = flags;
+  refshim_set_contiguous(&tf, 5, sz);
+  THIntTensor ti;
+  memset(&ti, 0, sizeof(ti));
+  long sz3[3] = {zsize, ysize, xsize};
+  ti.data = components;
+  refshim_set_contiguous(&ti, 3, sz3);
+  try {
+    tfluids_FloatFlagGrid fg(&tf, is_3d != 0);
+    std::vector<int32_t> csz;
+    const int n = findConnectedFluidComponents(fg, &ti, ibatch, &csz);
+    for (int i = 0; i < n && i < max_sizes; i++) sizes[i] = csz[i];
+    return n;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return -1;
+  }
+}
+
 int ref_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

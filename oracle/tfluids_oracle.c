@@ -984,6 +984,184 @@ float orc_jacobi(float* p, const float* flags, const float* div, const orc_dims*
 }
 
 /* ------------------------------------------------------------------------------------
+ * PCG pressure solve (a13).  The reference implementation is CUDA-only and sits on cuSPARSE /
+ * cuBLAS calls that CUDA 12 no longer has (generic/tfluids.cu:1245-1759), so this is a
+ * restatement of its ALGORITHM: per batch, per connected component of fluid cells
+ * (find_connected_fluid_components.cc:17-82; the labelling below follows that flood fill and is
+ * pinned against the compiled reference), the 7-point system of setupLaplacian (:909-1095: diag =
+ * number of non-obstacle neighbours, -1 towards fluid neighbours), Golub & Van Loan PCG with
+ * x0 = 0 (:1560-1725), preconditioner none / ilu0 / ic0 in the system's lexicographic order,
+ * components of one cell skipped, fewer than 5 cells un-preconditioned (:1386-1404), mean of the
+ * solution removed per component (:1735-1740).  For a symmetric matrix ILU(0) = L D L^T and
+ * IC(0) = (L D^1/2)(L D^1/2)^T are the same operator, so both names share one factor.
+ * Vectors are float, dot products accumulate in double (cuBLAS's order is unspecified).
+ * Parity for this function is by property, as in the reference's own test
+ * (test_tfluids.lua:836-905): residual < 2 tol, max |div| after the velocity update < 1e-4.
+ * ---------------------------------------------------------------------------------- */
+/* components: [nz][ny][nx] int32 for batch b, -1 for non-fluid; sizes: up to max_sizes entries.
+ * Returns the number of components.  Same numbering as the reference: components are numbered
+ * in the order a lexicographic scan (k, j, i) first meets them. */
+int orc_find_components(const float* flags, const orc_dims* d, int b, int* comp, int* sizes, int max_sizes) {
+  const long n = cells(d);
+  for (long c = 0; c < n; c++) comp[c] = -1;
+  long* stack = (long*)malloc(sizeof(long) * (size_t)(n > 0 ? n : 1));
+  int cur = 0;
+  const long sy = d->nx, sz = (long)d->nx * d->ny;
+  for (int k = 0; k < d->nz; k++) for (int j = 0; j < d->ny; j++) for (int i = 0; i < d->nx; i++) {
+    const long c0 = ((long)k * d->ny + j) * d->nx + i;
+    if (comp[c0] != -1 || !is_fluid(flags, d, b, k, j, i)) continue;
+    long top = 0, count = 0;
+    stack[top++] = c0;
+    comp[c0] = cur;
+    while (top > 0) {
+      const long c = stack[--top];
+      count++;
+      const int ci = (int)(c % d->nx), cj = (int)((c / d->nx) % d->ny), ck = (int)(c / sz);
+      const int di[6] = {-1, 1, 0, 0, 0, 0}, dj[6] = {0, 0, -1, 1, 0, 0}, dk[6] = {0, 0, 0, 0, -1, 1};
+      const int nn = d->is3d ? 6 : 4;
+      for (int q = 0; q < nn; q++) {
+        const int ii = ci + di[q], jj = cj + dj[q], kk = ck + dk[q];
+        if (ii < 0 || ii >= d->nx || jj < 0 || jj >= d->ny || kk < 0 || kk >= d->nz) continue;
+        const long cn = c + di[q] + dj[q] * sy + dk[q] * sz;
+        if (comp[cn] == -1 && is_fluid(flags, d, b, kk, jj, ii)) { comp[cn] = cur; stack[top++] = cn; }
+      }
+    }
+    if (cur < max_sizes) sizes[cur] = (int)count;
+    cur++;
+  }
+  free(stack);
+  return cur;
+}
+
+static inline double clamp_eps(double v) {              /* clampToEpsilon, generic/tfluids.cu:1153-1163 */
+  const double eps = 1.17549435e-38;                    /* std::numeric_limits<float>::min() */
+  if (fabs(v) < eps) return v < 0 ? -eps : eps;
+  return v;
+}
+
+/* precond: 0 none, 1 ilu0, 2 ic0.  Returns 0, or 1 when a fluid cell sits on the domain border
+ * (the reference raises "Non fluid cell found in a connected component", :1083-1090).
+ * residual: max over batches / components of ||r||_2 (-inf when nothing was solved, as :1343);
+ * iters: largest iteration count of any component. */
+int orc_pcg(float* p, const float* flags, const float* div, const orc_dims* d, int precond, float tol,
+            int max_iter, float* residual, int* iters) {
+  const long n = cells(d);
+  const long sy = d->nx, sz = (long)d->nx * d->ny;
+  memset(p, 0, sizeof(float) * n * d->nb);                                   /* :1337 */
+  int* comp = (int*)malloc(sizeof(int) * (size_t)n);
+  int* sizes = (int*)malloc(sizeof(int) * (size_t)(n / 1 + 1));
+  long* cell_of = (long*)malloc(sizeof(long) * (size_t)n);
+  int* sys = (int*)malloc(sizeof(int) * (size_t)n);
+  float *x = (float*)malloc(4 * (size_t)n), *r = (float*)malloc(4 * (size_t)n), *z = (float*)malloc(4 * (size_t)n),
+        *pp = (float*)malloc(4 * (size_t)n), *w = (float*)malloc(4 * (size_t)n), *pre = (float*)malloc(4 * (size_t)n),
+        *diag = (float*)malloc(4 * (size_t)n);
+  int (*nb6)[6] = (int (*)[6])malloc(sizeof(int) * 6 * (size_t)n);           /* xm, ym, zm, xp, yp, zp system index or -1 */
+  float worst = -INFINITY;
+  int worst_it = 0, rc = 0;
+  for (int b = 0; b < d->nb && !rc; b++) {
+    const int ncomp = orc_find_components(flags, d, b, comp, sizes, (int)n);
+    for (int ic = 0; ic < ncomp && !rc; ic++) {
+      if (sizes[ic] == 1) continue;                                           /* :1386-1392 */
+      const int use_pre = precond != 0 && sizes[ic] >= 5;                     /* :1399-1401 */
+      /* createReducedSystemIndices (:864-905): lexicographic numbering of the component. */
+      long m = 0;
+      for (long c = 0; c < n; c++) { sys[c] = -1; if (comp[c] == ic) { sys[c] = (int)m; cell_of[m++] = c; } }
+      for (long q = 0; q < m && !rc; q++) {
+        const long c = cell_of[q];
+        const int i = (int)(c % d->nx), j = (int)((c / d->nx) % d->ny), k = (int)(c / sz);
+        if (on_border(d, k, j, i, 1)) { rc = 1; break; }
+        float dg = 0.0f;
+        if (!is_obstacle(flags, d, b, k, j, i - 1)) dg += 1;
+        if (!is_obstacle(flags, d, b, k, j, i + 1)) dg += 1;
+        if (!is_obstacle(flags, d, b, k, j - 1, i)) dg += 1;
+        if (!is_obstacle(flags, d, b, k, j + 1, i)) dg += 1;
+        if (d->is3d && !is_obstacle(flags, d, b, k - 1, j, i)) dg += 1;
+        if (d->is3d && !is_obstacle(flags, d, b, k + 1, j, i)) dg += 1;
+        diag[q] = dg;
+        nb6[q][0] = is_fluid(flags, d, b, k, j, i - 1) ? sys[c - 1] : -1;
+        nb6[q][1] = is_fluid(flags, d, b, k, j - 1, i) ? sys[c - sy] : -1;
+        nb6[q][2] = (d->is3d && is_fluid(flags, d, b, k - 1, j, i)) ? sys[c - sz] : -1;
+        nb6[q][3] = is_fluid(flags, d, b, k, j, i + 1) ? sys[c + 1] : -1;
+        nb6[q][4] = is_fluid(flags, d, b, k, j + 1, i) ? sys[c + sy] : -1;
+        nb6[q][5] = (d->is3d && is_fluid(flags, d, b, k + 1, j, i)) ? sys[c + sz] : -1;
+        x[q] = 0.0f;
+        r[q] = div[(long)b * n + c];                                          /* copyDivergenceToSystem */
+      }
+      if (rc) break;
+      if (use_pre) {
+        /* IC(0) of the 7-point matrix: R_ii = sqrt(A_ii - sum_{k lower} R_ki^2), R_ij = -1 / R_ii; the
+         * level-0 pattern has no other update terms.  pre = 1 / R_ii. */
+        for (long q = 0; q < m; q++) {
+          float e = diag[q];
+          for (int t = 0; t < 3; t++) if (nb6[q][t] >= 0) { const float pk = pre[nb6[q][t]]; e = e - pk * pk; }
+          if (!(e > 1e-6f * diag[q])) e = diag[q];                           /* vanishing pivot guard */
+          pre[q] = 1.0f / sqrtf(e);
+        }
+      }
+      double rr = 0.0, rr0 = 0.0, rz = 0.0, rz_old = 0.0;
+      for (long q = 0; q < m; q++) rr += (double)r[q] * (double)r[q];
+      int iter = 0;
+      const double tol2 = (double)tol * (double)tol;
+      while (rr > tol2 && iter <= max_iter) {                                 /* :1588 */
+        if (use_pre) {
+          for (long q = 0; q < m; q++) {                                      /* R^T y = r */
+            float acc = r[q];
+            for (int t = 0; t < 3; t++) if (nb6[q][t] >= 0) acc = acc + pre[nb6[q][t]] * z[nb6[q][t]];
+            z[q] = acc * pre[q];
+          }
+          for (long q = m - 1; q >= 0; q--) {                                 /* R z = y */
+            float acc = 0.0f;
+            for (int t = 3; t < 6; t++) if (nb6[q][t] >= 0) acc = acc + z[nb6[q][t]];
+            z[q] = (z[q] + pre[q] * acc) * pre[q];
+          }
+          rz_old = rz;
+          rz = 0.0;
+          for (long q = 0; q < m; q++) rz += (double)r[q] * (double)z[q];
+        } else {
+          for (long q = 0; q < m; q++) z[q] = r[q];
+          rz_old = rr0;
+          rz = rr;
+        }
+        iter++;
+        if (iter == 1) {
+          for (long q = 0; q < m; q++) pp[q] = z[q];
+        } else {
+          const float beta = (float)(rz / clamp_eps(rz_old));
+          for (long q = 0; q < m; q++) pp[q] = z[q] + beta * pp[q];
+        }
+        double pw = 0.0;
+        for (long q = 0; q < m; q++) {
+          float acc = diag[q] * pp[q];
+          for (int t = 0; t < 6; t++) if (nb6[q][t] >= 0) acc = acc - pp[nb6[q][t]];
+          w[q] = acc;
+          pw += (double)pp[q] * (double)acc;
+        }
+        const float alpha = (float)(rz / clamp_eps(pw));
+        rr0 = rr;
+        rr = 0.0;
+        for (long q = 0; q < m; q++) {
+          x[q] = x[q] + alpha * pp[q];
+          r[q] = r[q] - alpha * w[q];
+          rr += (double)r[q] * (double)r[q];
+        }
+      }
+      const float res = (float)sqrt(rr);
+      if (res > worst) worst = res;
+      if (iter > worst_it) worst_it = iter;
+      double sum = 0.0;
+      for (long q = 0; q < m; q++) sum += (double)x[q];
+      const float mean = (float)(sum / (double)m);
+      for (long q = 0; q < m; q++) p[(long)b * n + cell_of[q]] = x[q] - mean;  /* copyPressureFromSystem */
+    }
+  }
+  free(comp); free(sizes); free(cell_of); free(sys); free(x); free(r); free(z); free(pp); free(w); free(pre);
+  free(diag); free(nb6);
+  if (residual) *residual = worst;
+  if (iters) *iters = worst_it;
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------
  * Lua-side pieces of the loop (lib/simulate.lua).
  * ---------------------------------------------------------------------------------- */
 /* x = x * invMask + bc  (setConstVals, lib/simulate.lua:136-158: cmul then add). */

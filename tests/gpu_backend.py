@@ -96,6 +96,13 @@ class GpuBackend:
         p[...] = host(t)
         return r
 
+    def solveLinearSystemPCG(self, p, flags, div, is3D, tol=1e-6, maxIter=1000, precondType="ic0"):
+        t = dev(p)
+        r = tfluids.solveLinearSystemPCG(t, dev(flags), dev(div), is3D, tol, maxIter, precondType)
+        self.last_pcg_iters = tfluids.solveLinearSystemPCG.last_iterations
+        p[...] = host(t)
+        return r
+
     def applyBC(self, x, invMask, bc):
         t = dev(x)
         tfluids.applyBC(t, dev(invMask), dev(bc))
