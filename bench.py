@@ -23,6 +23,7 @@ independent 128^3 grid (the batch-of-grids decomposition north_star allows); no 
 collective; time = max over ranks.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -360,6 +361,27 @@ def main():
                 extra.append({"kernel": "Jacobi x100 (k_jacobi_mask + 100 x k_jacobi_iter4), %d^3" % nj,
                               "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                               "ms": ms_j, "algorithmic_bytes_per_voxel_iter": 16})
+                if nj == 128:
+                    # ---- BASELINE config 4, second half: PCG, ic0, tol 1e-4, maxIter 100 (lib/simulate.lua:280-286).
+                    # Right-hand side = divergence of a wall-conditioned smooth velocity (compatible per component).
+                    Uj = torch.from_numpy(_synth.make_smooth_velocity(fl.cpu().numpy(), True, amp=2.0)).cuda()
+                    tfluids.setWallBcsForward(Uj, fl)
+                    tfluids.velocityDivergenceForward(Uj, fl, dv)
+                    res_p, it_p = ctypes.c_float(0), ctypes.c_int(0)
+                    for _ in range(2):
+                        flush.fill_(0.0)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        ctx.check(lib.tfl_solve_linear_system_pcg(ctx.h, tfluids._grid(pj), tfluids._grid(fl),
+                                                                  tfluids._grid(dv), 1, 2, 1e-4, 100,
+                                                                  ctypes.byref(res_p), ctypes.byref(it_p)))
+                        b.record(stream)
+                        stream.synchronize()
+                    extra.append({"kernel": "PCG ic0 tol 1e-4 maxIter 100 (k_sweep + k_direction_spmv + k_update per "
+                                            "iteration), 128^3", "bound": "latency (wavefront-sequential triangular solves)",
+                                  "ms": a.elapsed_time(b), "iterations": it_p.value, "residual": res_p.value,
+                                  "ms_per_iteration": a.elapsed_time(b) / max(it_p.value, 1)})
+                    del Uj
                 del fl, dv, pj
 
     if rank != 0:

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtfl.so")
+# TFL_LIB_PATH: a differently-tuned build of the same library (kernel experiments); still no fallback.
+LIB_PATH = os.environ.get("TFL_LIB_PATH") or os.path.join(HERE, "libtfl.so")
 
 
 class TflError(RuntimeError):

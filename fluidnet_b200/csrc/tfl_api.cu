@@ -543,6 +543,19 @@ int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
   return check_launch(ctx, "solveLinearSystemPCG");
 }
 
+// Debug hook (not in include/tfl.h): planes per CTA of the PCG sweep pipeline.
+extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
+  if (!ctx) return 1;
+  ctx->pcg.groups_override = groups;
+  return 0;
+}
+
+extern "C" int tfl_debug_pcg_timing(tfl_ctx* ctx, void* dev_buf) {
+  if (!ctx) return 1;
+  ctx->pcg.debug_timing = dev_buf;
+  return 0;
+}
+
 int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc) {
   if (!x || !inv_mask || !bc || !x->data || !inv_mask->data || !bc->data) return fail(ctx, "applyBC: nil tensor");
   if (!same_spatial(x, inv_mask) || !same_spatial(x, bc) || x->nc != inv_mask->nc || x->nc != bc->nc)

@@ -84,6 +84,8 @@ struct PcgScratch {            // owned by the context, grow-only
   unsigned long long epoch = 0;
   int* host = nullptr;         // pinned read-back words
   int sm_count = 0;
+  void* debug_timing = nullptr;   // debug: device buffer [chunks][4] of sweep timestamps
+  int groups_override = 0;     // debug: planes per CTA of the sweep kernel (0 = as many as fit)
 };
 size_t pcg_workspace_bytes(int nb, int nz, int ny, int nx);
 const char* pcg_status_string(int rc);

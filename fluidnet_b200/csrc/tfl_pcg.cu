@@ -305,6 +305,24 @@ __device__ __forceinline__ void st_release(unsigned long long* p, unsigned long 
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// Per-tick barrier of the compute warps and the gate warp (the talk warp never joins it).
+__device__ __forceinline__ void compute_barrier(int n_threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
 // Bounded wait: a stalled pipeline records a fault instead of hanging the device.
 __device__ __forceinline__ bool spin_expired(long long spins, int* faults) {
   if (spins > kSpinLimit) { atomicAdd(faults, 1); return true; }
@@ -323,6 +341,7 @@ struct SweepArgs {
   unsigned long long base;        // epoch offset of this launch
   double* rz;                     // per-component r.z accumulators
   int* faults;
+  unsigned long long* timing;     // debug: [chunk][4] globaltimer at fwd start / end, bwd start / end (or null)
 };
 
 // One CTA = GP thread groups of NYP threads; group gq works on plane chunk * GP + gq and runs one
@@ -331,89 +350,139 @@ struct SweepArgs {
 template <bool FACTOR>
 __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
   extern __shared__ float sh[];                 // [GP][2][W], W = NYP + 2, slot j + 1 = grid row j
+  __shared__ int sm_done;                       // ticks the compute warps have completed in this chunk
+  __shared__ int sm_avail;                      // steps of the neighbour chunk known to be complete
   const int W = g.NYP + 2;
   const int T = g.NYP;                          // threads per group
-  const int gq = threadIdx.x / T;               // group within the CTA
-  const int t = threadIdx.x - gq * T;           // grid row j owned by this thread
+  const int n_compute = g.GP * T;
+  // Two service warps behind the compute warps.  The GATE warp joins the per-tick barrier and then
+  // publishes the tick count to shared memory: it has no loads in flight, so its release store costs
+  // nothing (a compute thread's release would first wait for its own prefetches, one memory latency per
+  // tick).  The TALK warp (one lane) moves progress between shared memory and the global progress words.
+  const bool is_aux = (int)threadIdx.x >= n_compute;
+  const bool is_gate = is_aux && (int)threadIdx.x < n_compute + 32;
+  const int n_barrier = n_compute + 32;
+  const int gq = is_aux ? 0 : threadIdx.x / T;  // group within the CTA
+  const int j = threadIdx.x - gq * T;           // grid row owned by this thread
   for (int q = threadIdx.x; q < g.GP * 2 * W; q += blockDim.x) sh[q] = 0.0f;
-  __syncthreads();
-  unsigned long long seen = 0;                  // thread 0: last progress value read from the neighbour chunk
   const int ticks = g.S + g.GP - 1;
-  const int kPub = 4;
+  constexpr int kDepth = 3;                     // loads run kDepth ticks ahead of their use (ring of 4)
+  struct Slot { unsigned c; float r, pre, z, nb, nb2; };   // nb, nb2: values of the neighbour chunk's plane
+  Slot ring[4];
+
+  // Aux lane: forwards the neighbour chunk's progress word into sm_avail and this chunk's progress
+  // (sm_done, minus the lag of the plane the neighbour reads) into its own progress word.
+  const int ticks4_ = (ticks + 3) & ~3;
+  auto aux_loop = [&](const unsigned long long* their_word, unsigned long long* my_word) {
+    int published = 0, avail = 0;
+    long long spins = 0;
+    for (;;) {
+      const int d = ld_acquire_cta(&sm_done);
+      if (their_word && avail < g.S) {
+        const unsigned long long v = ld_acquire(their_word);
+        const int steps = v > a.base ? (int)min(v - a.base, (unsigned long long)g.S) : 0;
+        if (steps > avail) { avail = steps; st_release_cta(&sm_avail, avail); }
+      }
+      const int lead = min(d - (g.GP - 1), g.S);         // steps completed by the slowest group
+      if (lead > published) { st_release(my_word, a.base + (unsigned long long)lead); published = lead; }
+      if (d >= ticks4_) break;
+      if (spin_expired(++spins, a.faults)) break;
+    }
+  };
+  // Group that reads the neighbour chunk: block until `steps` of it are known complete.
+  auto need_steps = [&](int steps) {
+    steps = min(steps, g.S);
+    long long spins = 0;
+    while (ld_acquire_cta(&sm_avail) < steps) if (spin_expired(++spins, a.faults)) break;
+  };
+
+  // Arithmetic notes for both sweeps.  A neighbour that is in the system is always linked (fluid
+  // neighbours belong to the same component) and one that is not contributes an exchanged value of 0,
+  // so no link bits are tested: the exchanged values are simply added.  Cells of un-preconditioned
+  // components (pre = 1) exchange 0 so that they reduce to z = r, and cells outside the system have
+  // pre = 0, which makes their results 0.  In 2-D the planes of a CTA are different batch elements and
+  // the z term is switched off.
+  const int ticks4 = (ticks + 3) & ~3;          // the tick loops are unrolled by 4; surplus ticks do nothing
+  const float use_z = g.is3d ? 1.0f : 0.0f;
 
   // ---------------- forward: R^T y = r (or the factor) ----------------
   for (int chunk = blockIdx.x; chunk < g.chunks; chunk += gridDim.x) {
-    const int pl = chunk * g.GP + gq;
-    const bool plane_ok = pl < g.P;
     const bool wait_below = g.is3d && chunk > 0;
-    float carry = 0.0f;                          // this row's previous cell
-    if (threadIdx.x == 0 && wait_below) {       // step 0 of group 0 needs step 0 of the plane below
-      long long spins = 0;
-      while ((seen = ld_acquire(a.prog_f + chunk - 1)) < a.base + 1) if (spin_expired(++spins, a.faults)) break;
-    }
+    if (threadIdx.x == 0) { sm_done = 0; sm_avail = 0; }
     __syncthreads();
-    for (int tick = 0; tick < ticks; tick++) {
-      const int s = tick - gq;
-      const int cur = tick & 1, prv = cur ^ 1;
-      float* mine = sh + (gq * 2 + cur) * W;
-      const float* mine_prev = sh + (gq * 2 + prv) * W;
-      const float* below_prev = gq > 0 ? sh + ((gq - 1) * 2 + prv) * W : nullptr;
-      {
-        const int j = t;
-        float out = 0.0f;
-        if (plane_ok && s >= 0 && s < g.S && j < g.ny) {
-          const int i = s - j;
-          if (i >= 0 && i < g.nx) {
-            const long long q = ((long long)pl * g.S + s) * g.NYP + j;
-            const unsigned c = a.cf[q];
-            if (c & kInSys) {
-              const bool on = (c & kPreOn) != 0;
-              if (FACTOR) {
-                const float dg = (float)((c >> kDiagShift) & 7u);
-                float e = dg;
-                if (on) {
-                  if (c & kXM) e -= carry * carry;
-                  if (c & kYM) { const float v = mine_prev[j]; e -= v * v; }
-                  if (c & kZM) { const float v = gq > 0 ? below_prev[j + 1] : __ldcg(a.pre + q - g.plane); e -= v * v; }
-                  if (!(e > 1e-6f * dg)) e = dg;                 // vanishing pivot guard
-                }
-                out = on ? 1.0f / sqrtf(e) : 1.0f;
-                __stcg(a.pre + q, out);
-              } else {
-                float acc = a.r[q];
-                if (on) {
-                  if (c & kXM) acc += carry;
-                  if (c & kYM) acc += mine_prev[j];
-                  if (c & kZM) acc += gq > 0 ? below_prev[j + 1] : __ldcg(a.pre + q - g.plane) * __ldcg(a.z + q - g.plane);
-                }
-                const float pv = a.pre[q];
-                const float y = acc * pv;
-                __stcg(a.z + q, y);
-                out = pv * y;
-              }
-            }
+    if (a.timing && threadIdx.x == 0) a.timing[chunk * 4 + 0] = global_ns();
+    if (is_aux) {
+      if (is_gate) {
+        for (int tick = 0; tick < ticks4; tick++) {
+          compute_barrier(n_barrier);
+          if (threadIdx.x == n_compute) st_release_cta(&sm_done, tick + 1);
+        }
+      } else if (threadIdx.x == n_compute + 32) {
+        aux_loop(wait_below ? a.prog_f + chunk - 1 : nullptr, a.prog_f + chunk);
+      }
+    } else {
+      const int pl = chunk * g.GP + gq;
+      const bool plane_ok = pl < g.P && j < g.ny;
+      const bool from_global = wait_below && gq == 0;
+      const long long plane0 = (long long)pl * g.S * g.NYP + j;
+      const unsigned short* p_cf = a.cf + plane0;
+      const float* p_r = a.r + plane0;
+      float* p_pre = a.pre + plane0;
+      float* p_z = a.z + plane0;
+      float* sm = sh + gq * 2 * W + j;           // sm[1 + parity * W] = this row's exchange slot
+      const int below_off = gq > 0 ? 1 - 2 * W : 0;   // same slot of the group one plane below (previous parity)
+      // Everything step s of this thread needs from global memory.
+      auto fetch = [&](int tick) {
+        Slot f;
+        f.c = 0; f.r = 0.0f; f.pre = 0.0f; f.z = 0.0f; f.nb = 0.0f; f.nb2 = 0.0f;
+        const int s = tick - gq;
+        if (plane_ok && (unsigned)s < (unsigned)g.S) {
+          const int off = s * g.NYP;
+          f.c = p_cf[off];
+          if (!FACTOR) { f.r = p_r[off]; f.pre = p_pre[off]; }
+          if (from_global) {                   // no arithmetic here: a use would wait for the loads
+            f.nb = __ldcg(p_pre + off - g.plane);
+            f.nb2 = FACTOR ? 1.0f : __ldcg(p_z + off - g.plane);
           }
         }
-        carry = out;
-        mine[j + 1] = out;
-      }
-      // Progress of the chunk below needed by group 0 at the next tick.
-      if (threadIdx.x == 0 && wait_below && tick + 1 < g.S) {
-        const unsigned long long need = a.base + (unsigned long long)(tick + 2);
-        long long spins = 0;
-        while (seen < need) {
-          seen = ld_acquire(a.prog_f + chunk - 1);
-          if (spin_expired(++spins, a.faults)) break;
+        return f;
+      };
+      float carry = 0.0f;                        // this row's previous cell
+      if (from_global) need_steps(kDepth);
+#pragma unroll
+      for (int u = 0; u < kDepth; u++) ring[u] = fetch(u);
+      for (int tick0 = 0; tick0 < ticks4; tick0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int tick = tick0 + u;
+          if (from_global) need_steps(tick + kDepth + 1);
+          ring[(u + kDepth) & 3] = fetch(tick + kDepth);
+          const Slot f = ring[u];
+          const int prv = (u & 1) ^ 1;            // tick0 is a multiple of 4: parities are compile-time
+          const float ym = sm[prv * W];
+          const float zm = (gq > 0 ? sm[prv * W + below_off] : f.nb * f.nb2) * use_z;
+          const float on = (f.c & kPreOn) ? 1.0f : 0.0f;
+          float out;
+          if (FACTOR) {
+            const float dg = (float)((f.c >> kDiagShift) & 7u);
+            float e = dg - carry * carry - ym * ym - zm * zm;
+            if (!(e > 1e-6f * dg)) e = dg;                     // vanishing pivot guard
+            const float pv = on != 0.0f ? 1.0f / sqrtf(e) : 1.0f;
+            if (f.c & kInSys) __stcg(p_pre + (tick - gq) * g.NYP, pv);
+            out = on * pv;
+          } else {
+            const float y = (f.r + carry + ym + zm) * f.pre;
+            if (f.c & kInSys) __stcg(p_z + (tick - gq) * g.NYP, y);
+            out = on * f.pre * y;
+          }
+          carry = out;
+          sm[1 + (u & 1) * W] = out;
+          compute_barrier(n_barrier);
         }
       }
-      __syncthreads();
-      // Steps completed by the top plane of this chunk.
-      const int top_done = tick - (g.GP - 1) + 1;
-      if (threadIdx.x == 0 && top_done > 0 && (top_done % kPub == 0 || top_done == g.S)) {
-        __threadfence();
-        st_release(a.prog_f + chunk, a.base + (unsigned long long)top_done);
-      }
     }
+    __syncthreads();
+    if (a.timing && threadIdx.x == 0) a.timing[chunk * 4 + 1] = global_ns();
   }
   if (FACTOR) return;
 
@@ -421,68 +490,78 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
   CompAcc racc;
   const int my_last = blockIdx.x + ((g.chunks - 1 - blockIdx.x) / gridDim.x) * gridDim.x;   // highest chunk of this CTA
   for (int chunk = my_last; chunk >= 0; chunk -= gridDim.x) {
-    const int pl = chunk * g.GP + gq;
-    const bool plane_ok = pl < g.P;
     const bool wait_above = g.is3d && chunk < g.chunks - 1;
-    const int lag = g.GP - 1 - gq;              // the top group leads
-    float carry = 0.0f;                          // this row's previous cell
-    __syncthreads();
+    if (threadIdx.x == 0) { sm_done = 0; sm_avail = 0; }
     for (int q = threadIdx.x; q < g.GP * 2 * W; q += blockDim.x) sh[q] = 0.0f;
-    seen = 0;
-    if (threadIdx.x == 0 && wait_above) {
-      long long spins = 0;
-      while ((seen = ld_acquire(a.prog_b + chunk + 1)) < a.base + 1) if (spin_expired(++spins, a.faults)) break;
+    __syncthreads();
+    if (a.timing && threadIdx.x == 0) a.timing[chunk * 4 + 2] = global_ns();
+    if (is_aux) {
+      if (is_gate) {
+        for (int tick = 0; tick < ticks4; tick++) {
+          compute_barrier(n_barrier);
+          if (threadIdx.x == n_compute) st_release_cta(&sm_done, tick + 1);
+        }
+      } else if (threadIdx.x == n_compute + 32) {
+        aux_loop(wait_above ? a.prog_b + chunk + 1 : nullptr, a.prog_b + chunk);
+      }
+    } else {
+      const int pl = chunk * g.GP + gq;
+      const bool plane_ok = pl < g.P && j < g.ny;
+      const bool from_global = wait_above && gq == g.GP - 1;
+      const int lag = g.GP - 1 - gq;            // the top group leads
+      const long long plane0 = (long long)pl * g.S * g.NYP + j;
+      const unsigned short* p_cf = a.cf + plane0;
+      const float* p_r = a.r + plane0;
+      const float* p_pre = a.pre + plane0;
+      float* p_z = a.z + plane0;
+      const int* p_comp = a.comp + plane0;
+      float* sm = sh + gq * 2 * W + j;
+      const int above_off = gq < g.GP - 1 ? 1 + 2 * W : 0;
+      auto fetch = [&](int tick) {
+        Slot f;
+        f.c = 0; f.r = 0.0f; f.pre = 0.0f; f.z = 0.0f; f.nb = 0.0f; f.nb2 = 0.0f;
+        const int st = tick - lag;
+        if (plane_ok && (unsigned)st < (unsigned)g.S) {
+          const int off = (g.S - 1 - st) * g.NYP;
+          f.c = p_cf[off];
+          f.r = p_r[off];
+          f.pre = p_pre[off];
+          f.z = __ldcg(p_z + off);              // y of the forward sweep (written by this thread)
+          if (from_global) f.nb = __ldcg(p_z + off + g.plane);
+        }
+        return f;
+      };
+      float carry = 0.0f;
+      if (from_global) need_steps(kDepth);
+#pragma unroll
+      for (int u = 0; u < kDepth; u++) ring[u] = fetch(u);
+      for (int tick0 = 0; tick0 < ticks4; tick0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int tick = tick0 + u;
+          if (from_global) need_steps(tick + kDepth + 1);
+          ring[(u + kDepth) & 3] = fetch(tick + kDepth);
+          const Slot f = ring[u];
+          const int prv = (u & 1) ^ 1;
+          const float yp = sm[prv * W + 2];
+          const float zp = (gq < g.GP - 1 ? sm[prv * W + above_off] : f.nb) * use_z;
+          const float on = (f.c & kPreOn) ? 1.0f : 0.0f;
+          const float out = (f.z + f.pre * on * (carry + yp + zp)) * f.pre;
+          if (f.c & kInSys) {
+            const int off = (g.S - 1 - (tick - lag)) * g.NYP;
+            __stcg(p_z + off, out);
+            racc.add(a.rz, p_comp[off], (double)f.r * (double)out);
+          }
+          carry = out;
+          sm[1 + (u & 1) * W] = out;
+          compute_barrier(n_barrier);
+        }
+      }
     }
     __syncthreads();
-    for (int tick = 0; tick < ticks; tick++) {
-      const int st = tick - lag;                // step counter of this group
-      const int s = g.S - 1 - st;
-      const int cur = tick & 1, prv = cur ^ 1;
-      float* mine = sh + (gq * 2 + cur) * W;
-      const float* mine_prev = sh + (gq * 2 + prv) * W;
-      const float* above_prev = gq < g.GP - 1 ? sh + ((gq + 1) * 2 + prv) * W : nullptr;
-      {
-        const int j = t;
-        float out = 0.0f;
-        if (plane_ok && st >= 0 && st < g.S && j < g.ny) {
-          const int i = s - j;
-          if (i >= 0 && i < g.nx) {
-            const long long q = ((long long)pl * g.S + s) * g.NYP + j;
-            const unsigned c = a.cf[q];
-            if (c & kInSys) {
-              float acc = 0.0f;
-              if (c & kPreOn) {
-                if (c & kXP) acc += carry;
-                if (c & kYP) acc += mine_prev[j + 2];
-                if (c & kZP) acc += gq < g.GP - 1 ? above_prev[j + 1] : __ldcg(a.z + q + g.plane);
-              }
-              const float pv = a.pre[q];
-              out = (__ldcg(a.z + q) + pv * acc) * pv;
-              __stcg(a.z + q, out);
-              racc.add(a.rz, a.comp[q], (double)a.r[q] * (double)out);
-            }
-          }
-        }
-        carry = out;
-        mine[j + 1] = out;
-      }
-      if (threadIdx.x == 0 && wait_above && tick + 1 < g.S) {
-        const unsigned long long need = a.base + (unsigned long long)(tick + 2);
-        long long spins = 0;
-        while (seen < need) {
-          seen = ld_acquire(a.prog_b + chunk + 1);
-          if (spin_expired(++spins, a.faults)) break;
-        }
-      }
-      __syncthreads();
-      const int bottom_done = tick - (g.GP - 1) + 1;     // group 0 lags the most
-      if (threadIdx.x == 0 && bottom_done > 0 && (bottom_done % kPub == 0 || bottom_done == g.S)) {
-        __threadfence();
-        st_release(a.prog_b + chunk, a.base + (unsigned long long)bottom_done);
-      }
-    }
+    if (a.timing && threadIdx.x == 0) a.timing[chunk * 4 + 3] = global_ns();
   }
-  warp_comp_add(a.rz, racc.comp, racc.v);
+  if (!is_aux) warp_comp_add(a.rz, racc.comp, racc.v);
 }
 
 inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
@@ -503,7 +582,7 @@ const char* pcg_status_string(int rc) {
     case 1: return "Non fluid cell found in a connected component or fluid cell found on the domain border";
     case 2: return "PCG Error: residual is nan!";
     case 3: return "PCG: CUDA error";
-    case 4: return "PCG: grid too large for the sweep kernel (ny > 1024)";
+    case 4: return "PCG: grid too large for the sweep kernel (ny > 960)";
     case 5: return "PCG: internal error, sweep pipeline stalled";
     default: return "PCG: unknown error";
   }
@@ -521,8 +600,9 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   g.n = (long long)nz * ny * nx;
   g.plane = (long long)g.S * g.NYP;
   g.slots = (long long)g.P * g.plane;
-  if (g.NYP > 1024) return 4;
-  g.GP = 1024 / g.NYP;
+  if (g.NYP > 960) return 4;
+  g.GP = (1024 - 64) / g.NYP;      // two service warps per CTA (gate, talk)
+  if (sc.groups_override > 0 && sc.groups_override < g.GP) g.GP = sc.groups_override;
   if (g.GP > g.P) g.GP = g.P;
   g.chunks = (g.P + g.GP - 1) / g.GP;
   const long long cells = g.n * nb;
@@ -607,7 +687,8 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   sa.cf = cf; sa.comp = comp; sa.r = r; sa.z = z; sa.pre = pre;
   sa.prog_f = sc.prog; sa.prog_b = sc.prog + g.chunks;
   sa.rz = cs.rz_new; sa.faults = header + 2;
-  const int sweep_threads = g.GP * g.NYP;
+  sa.timing = (unsigned long long*)sc.debug_timing;
+  const int sweep_threads = g.GP * g.NYP + 64;
   const size_t sweep_smem = (size_t)g.GP * 2 * (g.NYP + 2) * sizeof(float);
   int occ = 0;
   PCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep<false>, sweep_threads, sweep_smem));
@@ -630,16 +711,21 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   PCG_CUDA(cudaStreamSynchronize(st));
   float* p_old = p0;
   float* p_new = p1;
+  // The host only needs to learn when every component has terminated; termination itself (tolerance or
+  // iteration cap) is decided per component on the device, so reading back every 4th iteration changes
+  // nothing in the result -- iterations past a component's end are no-ops for it.
   while (sc.host[0] > 0 && !sc.host[1] && !sc.host[2]) {
-    PCG_CUDA(cudaMemsetAsync(header, 0, 4, st));
-    if (!no_precond) PCG_CUDA(launch_sweep(false));
-    k_direction_spmv<<<ew_blocks, 256, 0, st>>>(cf, comp, no_precond ? r : z, p_old, p_new, w, cs, g, no_precond);
-    k_update<<<ew_blocks, 256, 0, st>>>(cf, comp, p_new, w, x, r, cs, g.slots, no_precond);
-    k_scalars<<<(ncomp + 255) / 256, 256, 0, st>>>(cs, ncomp, tol2, max_iter, 0, no_precond);
-    *launches += 3;
+    for (int rep = 0; rep < 4; rep++) {
+      PCG_CUDA(cudaMemsetAsync(header, 0, 4, st));
+      if (!no_precond) PCG_CUDA(launch_sweep(false));
+      k_direction_spmv<<<ew_blocks, 256, 0, st>>>(cf, comp, no_precond ? r : z, p_old, p_new, w, cs, g, no_precond);
+      k_update<<<ew_blocks, 256, 0, st>>>(cf, comp, p_new, w, x, r, cs, g.slots, no_precond);
+      k_scalars<<<(ncomp + 255) / 256, 256, 0, st>>>(cs, ncomp, tol2, max_iter, 0, no_precond);
+      *launches += 3;
+      float* tswap = p_old; p_old = p_new; p_new = tswap;
+    }
     PCG_CUDA(cudaMemcpyAsync(sc.host, header, 16, cudaMemcpyDeviceToHost, st));
     PCG_CUDA(cudaStreamSynchronize(st));
-    float* tswap = p_old; p_old = p_new; p_new = tswap;
   }
   if (sc.host[2]) return 5;
   if (sc.host[1]) return 2;

@@ -475,8 +475,16 @@ __device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const f
   return r;
 }
 
+// Resident CTAs per SM the advectVel kernels are compiled for (register budget 65536 / 256 / N).
+#ifndef TFL_ADVECT_MINB1
+#define TFL_ADVECT_MINB1 4
+#endif
+#ifndef TFL_ADVECT_MINB2
+#define TFL_ADVECT_MINB2 4
+#endif
+
 template <bool IS3D, typename FT, bool OURS>
-__global__ void __launch_bounds__(256, 4) k_advect_vel_pass1(const float* __restrict__ U, const FT* __restrict__ flags,
+__global__ void __launch_bounds__(256, TFL_ADVECT_MINB1) k_advect_vel_pass1(const float* __restrict__ U, const FT* __restrict__ flags,
                                    float* __restrict__ out, float dt, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
@@ -516,7 +524,7 @@ __device__ __forceinline__ float clamp_component_mac(const float* __restrict__ o
 // Backward pass on the forward field + MacCormackCorrectMAC + MacCormackClampMAC, fused
 // (third_party/tfluids.cc:859-915, 660-774).
 template <bool IS3D, typename FT, bool OURS>
-__global__ void __launch_bounds__(256, 4) k_advect_vel_pass2(const float* __restrict__ U, const float* __restrict__ fwd,
+__global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(const float* __restrict__ U, const float* __restrict__ fwd,
                                    const FT* __restrict__ flags, float* __restrict__ dst, float dt,
                                    float strength, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);

@@ -31,11 +31,30 @@ else:
         tfluids.setWallBcsForward(u, f)
         d = torch.zeros_like(f); tfluids.velocityDivergenceForward(u, f, d)
         p = torch.zeros_like(f)
-        for precond in ("ic0", "none"):
+        for precond, gp in (("ic0", 0), ("ic0", 1), ("ic0", 2), ("ic0", 3), ("ic0", 4), ("ic0", 5), ("none", 0)):
+            c = tfluids.context()
+            c.lib.tfl_debug_pcg_groups(c.h, gp)
             for rep in range(2):
                 torch.cuda.synchronize(); t0 = time.time()
                 res = tfluids.solveLinearSystemPCG(p, f, d, True, 1e-4, 100, precond)
                 torch.cuda.synchronize(); t1 = time.time()
             it = tfluids.solveLinearSystemPCG.last_iterations
-            print("n=%d %s: %.2f ms, %d iterations (%.3f ms/iter), residual %g" % (
-                n, precond, (t1 - t0) * 1e3, it, (t1 - t0) * 1e3 / max(it, 1), res), flush=True)
+            print("n=%d %s gp=%d: %.2f ms, %d iterations (%.3f ms/iter), residual %g" % (
+                n, precond, gp, (t1 - t0) * 1e3, it, (t1 - t0) * 1e3 / max(it, 1), res), flush=True)
+
+    # pipeline picture of the LAST sweep of a solve (n = 128, default groups)
+    import ctypes as C
+    c = tfluids.context()
+    c.lib.tfl_debug_pcg_groups(c.h, 0)
+    buf = torch.zeros(64 * 4, dtype=torch.int64, device="cuda")
+    c.lib.tfl_debug_pcg_timing.argtypes = [C.c_void_p, C.c_void_p]
+    c.lib.tfl_debug_pcg_timing(c.h, C.c_void_p(buf.data_ptr()))
+    tfluids.solveLinearSystemPCG(p, f, d, True, 1e-4, 8, "ic0")
+    torch.cuda.synchronize()
+    c.lib.tfl_debug_pcg_timing(c.h, None)
+    t = buf.cpu().numpy().reshape(-1, 4)
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    print("chunk: fwd start, fwd end, bwd start, bwd end (us)")
+    for i, row in enumerate(t):
+        print(i, " ".join("%8.1f" % ((v - t0) / 1e3) for v in row))
