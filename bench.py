@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, default=N_GRID)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Jacobi / PCG side measurements (kernel experiments)")
     ap.add_argument("--mode", default="grids", choices=["grids", "slab"],
                     help="grids: one independent --grid^3 domain per GPU (weak scaling, the default and the "
                          "BASELINE metric); slab: ONE --grid^3 domain z-slab decomposed over the GPUs with NCCL "
@@ -341,7 +342,7 @@ def main():
 
         # ---- BASELINE config 4: 100-iteration Jacobi sweep (stencil HBM roofline) ----------
         extra = []
-        if rank == 0:
+        if rank == 0 and not args.no_extra:
             from fluidnet_b200 import synth as _synth
             for nj in (128, 256):
                 fl = torch.from_numpy(_synth.make_flags(nj, nj, nj, True, nb=1, geometry=True)).cuda()

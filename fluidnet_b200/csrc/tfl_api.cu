@@ -32,6 +32,16 @@ struct tfl_ctx {
   int slab_margin = 2;                      // extra planes on which forward passes are evaluated
   cudaStream_t side_stream = nullptr;       // density advection runs beside velocity advection
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Host-buffer step (tfl_host_sim_step): copies run on their own streams and the step waits for each
+  // input only where it is first read / hands each output over as soon as it is final.
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_u_in = nullptr, ev_d_in = nullptr, ev_p_in = nullptr, ev_d_ready = nullptr, ev_d_out = nullptr;
+  struct {
+    bool active = false;
+    float* density_host = nullptr;          // where the advected density goes once it is final
+    size_t density_bytes = 0;
+    bool density_sent = false;
+  } ov;
   PcgScratch pcg;                           // grow-only buffers of the PCG solve
 };
 
@@ -198,6 +208,10 @@ int tfl_create(tfl_ctx** out, int device) {
   cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking);
+  for (cudaEvent_t* e : {&c->ev_u_in, &c->ev_d_in, &c->ev_p_in, &c->ev_d_ready, &c->ev_d_out})
+    cudaEventCreateWithFlags(e, cudaEventDisableTiming);
   *out = c;
   return 0;
 }
@@ -213,6 +227,8 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (cudaStream_t q : {ctx->copy_in, ctx->copy_out}) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
+  for (cudaEvent_t e : {ctx->ev_u_in, ctx->ev_d_in, ctx->ev_p_in, ctx->ev_d_ready, ctx->ev_d_out}) if (e) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -867,11 +883,14 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   // Byte copy of the flags for this step (every bit the kernels test is below 256).
   launch_flags_to_u8(s->flags.data, fl8, (long long)cells, st);
   ctx->launches += 1;
+  const bool ov = ctx->ov.active;
+  if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_u_in, 0));          // U has arrived from the host
   if (has_density) {
     // Density and velocity advection are independent (both read the old U): run the density
     // kernels on a side stream so the two latency-bound kernel pairs overlap.
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_d_in, 0));
     const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, mc->advection_method, 0,
                                         mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
     if (nl < 0) return fail(ctx, "advectScalar: bad method");
@@ -901,6 +920,16 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
                      d_bc ? s->density_bc_inv_mask.data : nullptr, d_bc ? s->density_bc.data : nullptr, do_buoy, bs,
                      g, st);
   ctx->launches += 1;
+  if (ov && has_density && ctx->ov.density_host) {
+    // The density is final here (nothing later in the step writes it): send it home while the
+    // vorticity / projection kernels run.
+    TFL_CUDA(ctx, cudaEventRecord(ctx->ev_d_ready, st));
+    TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_d_ready, 0));
+    TFL_CUDA(ctx, cudaMemcpyAsync(ctx->ov.density_host, s->density.data, ctx->ov.density_bytes, cudaMemcpyDeviceToHost,
+                                  ctx->copy_out));
+    TFL_CUDA(ctx, cudaEventRecord(ctx->ev_d_out, ctx->copy_out));
+    ctx->ov.density_sent = true;
+  }
   if (mc->gravity_scale > 0.0) {
     const float k = (float)((-dx / 4.0) * mc->gravity_scale);
     const float scale_dt = mc->dt / get_dx(g);
@@ -919,6 +948,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   launch_vort_bc_mask(s->U.data, fl8, force, do_vort, u_bc ? s->U_bc_inv_mask.data : nullptr,
                       u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
   const ConvTcGeo& tg = m->act_geo;
+  if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_p_in, 0));          // pDiv is first read here
   launch_cnn_inputs_fused(s->p.data, s->U.data, fl8, sums, mc->normalize_input_threshold, scale, m->act[0],
                           tg.px, tg.py, g, st);
   run_conv_stack(m, p_net, st);
@@ -1047,14 +1077,35 @@ int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float*
   if (!hs || !p || !U) return fail(ctx, "host_sim_step: nil buffer");
   cudaStream_t st = ctx->stream;
   tfl_state s = hs->st;
-  TFL_CUDA(ctx, cudaMemcpyAsync(s.p.data, p, hs->cells * 4, cudaMemcpyHostToDevice, st));
-  TFL_CUDA(ctx, cudaMemcpyAsync(s.U.data, U, hs->cells * 4 * hs->nc, cudaMemcpyHostToDevice, st));
-  if (density) TFL_CUDA(ctx, cudaMemcpyAsync(s.density.data, density, hs->cells * 4, cudaMemcpyHostToDevice, st));
-  else s.density.data = nullptr;
-  if (tfl_simulate_step(ctx, &s, mc, cnn)) return 1;
-  TFL_CUDA(ctx, cudaMemcpyAsync(p, s.p.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  if (!density) s.density.data = nullptr;
+  // Inputs in the order the step reads them: U (both advections), density (density advection), pDiv
+  // (network input, much later).  One copy stream keeps them in that order on the PCIe link.
+  TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));                      // earlier work on the step stream
+  TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
+  TFL_CUDA(ctx, cudaMemcpyAsync(s.U.data, U, hs->cells * 4 * hs->nc, cudaMemcpyHostToDevice, ctx->copy_in));
+  TFL_CUDA(ctx, cudaEventRecord(ctx->ev_u_in, ctx->copy_in));
+  if (density) TFL_CUDA(ctx, cudaMemcpyAsync(s.density.data, density, hs->cells * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+  TFL_CUDA(ctx, cudaEventRecord(ctx->ev_d_in, ctx->copy_in));
+  TFL_CUDA(ctx, cudaMemcpyAsync(s.p.data, p, hs->cells * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+  TFL_CUDA(ctx, cudaEventRecord(ctx->ev_p_in, ctx->copy_in));
+  const bool fused = mc->sim_method == TFL_SIM_CONVNET && cnn && cnn->tc_ok && cnn->mode > 0 && !ctx->slab &&
+                     hs->st.flags.nb == 1 && mc->advection_method >= 0 && mc->advection_method <= 5;
+  ctx->ov.active = fused;
+  ctx->ov.density_host = density;
+  ctx->ov.density_bytes = hs->cells * 4;
+  ctx->ov.density_sent = false;
+  if (!fused) {                                                           // operator-by-operator path: no overlap
+    TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_p_in, 0));
+  }
+  const int rc = tfl_simulate_step(ctx, &s, mc, cnn);
+  const bool density_sent = ctx->ov.density_sent;
+  ctx->ov.active = false;
+  if (rc) { cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(ctx->copy_out); return 1; }
   TFL_CUDA(ctx, cudaMemcpyAsync(U, s.U.data, hs->cells * 4 * hs->nc, cudaMemcpyDeviceToHost, st));
-  if (density) TFL_CUDA(ctx, cudaMemcpyAsync(density, s.density.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  TFL_CUDA(ctx, cudaMemcpyAsync(p, s.p.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  if (density && !density_sent)
+    TFL_CUDA(ctx, cudaMemcpyAsync(density, s.density.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
+  if (density_sent) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d_out, 0));
   TFL_CUDA(ctx, cudaStreamSynchronize(st));
   return 0;
 }

@@ -126,6 +126,39 @@ def test_fused_equals_operator_sequence():
         close(a[k].cpu().numpy(), b[k].cpu().numpy(), 1e-6, k)
 
 
+@pytest.mark.parametrize("method", ["convnet", "jacobi"])
+def test_host_buffer_step_equals_device_step(method):
+    """tfl_host_sim_step (pinned host buffers in and out, the copies overlapped with the fused step)
+    returns what tfl_simulate_step leaves on the device, over several steps."""
+    import ctypes as C
+    import torch
+    from fluidnet_b200 import simulate, tfluids
+    from gpu_backend import make_gpu_model
+    n = 32
+    batch = make_batch(n, True)
+    gm = make_gpu_model(synth.make_model(True))
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=0.5,
+                                 vorticityConfinementAmp=3.0, simMethod=method, maxIter=20)
+    dev_batch = to_gpu(batch)
+    ctx = tfluids.context()
+    lib = ctx.lib
+    hs = C.c_void_p()
+    keep = [np.ascontiguousarray(batch[k]) for k in ("flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask")]
+    ctx.check(lib.tfl_host_sim_create(ctx.h, 1, n, n, n, 1, *[a.ctypes.data for a in keep], C.byref(hs)))
+    hp = torch.from_numpy(batch["pDiv"].copy()).pin_memory()
+    hU = torch.from_numpy(batch["UDiv"].copy()).pin_memory()
+    hd = torch.from_numpy(batch["density"].copy()).pin_memory()
+    mc = simulate.make_mconf(mconf)
+    try:
+        for step in range(3):
+            simulate.simulate_fused(None, mconf, dev_batch, gm)
+            ctx.check(lib.tfl_host_sim_step(ctx.h, hs, hp.data_ptr(), hU.data_ptr(), hd.data_ptr(), C.byref(mc), gm.h))
+            for k, h in (("density", hd), ("UDiv", hU), ("pDiv", hp)):
+                close(h.numpy(), dev_batch[k].cpu().numpy(), 1e-6, "step %d %s" % (step, k))
+    finally:
+        lib.tfl_host_sim_destroy(ctx.h, hs)
+
+
 def test_full_size_properties():
     """BASELINE-size (128^3) checks that do not need the CPU oracle: the Jacobi-projected
     velocity is (nearly) divergence free, the obstacle faces stay exactly zero, advection of
