@@ -559,6 +559,65 @@ int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
   return check_launch(ctx, "solveLinearSystemPCG");
 }
 
+int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, int is_3d) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p")) return 1;
+  if (!same_spatial(flags, p)) return fail(ctx, "size mismatch");
+  if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
+  if (ctx->slab) return fail(ctx, "normalizePressureMean: single GPU only (connected components span the slabs)");
+  if ((long long)flags->nb * flags->nz * flags->ny * flags->nx >= (1ll << 31)) return fail(ctx, "grid too large");
+  if (arena_reserve(ctx, pcg_workspace_bytes(flags->nb, flags->nz, flags->ny, flags->nx))) return 1;
+  if (normalize_pressure_mean(ctx->arena, p->data, flags->data, flags->nb, flags->nz, flags->ny, flags->nx, is_3d,
+                              &ctx->launches, ctx->stream))
+    return fail(ctx, "normalizePressureMean: %s", cudaGetErrorString(cudaGetLastError()));
+  return check_launch(ctx, "normalizePressureMean");
+}
+
+int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* out) {
+  if (!in || !out || !in->data || !out->data) return fail(ctx, "ERROR: input and output must be dim 5");
+  if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
+  if (out->nb != in->nb || out->nc != in->nc || out->nz != in->nz * ratio || out->ny != in->ny * ratio ||
+      out->nx != in->nx * ratio)
+    return fail(ctx, "ERROR: input : output size mismatch.");             // generic/tfluids.cc:528-532
+  launch_upsample_nearest(in->data, out->data, in->nb * in->nc, in->nz, in->ny, in->nx, ratio, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "volumetricUpSamplingNearestForward");
+}
+
+int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst) {
+  if (!src || !dst || !src->data || !dst->data) return fail(ctx, "ERROR: src and dst must be dim 5");
+  if (!same_spatial(src, dst) || src->nc != dst->nc) return fail(ctx, "size mismatch");
+  if (blur_rad <= 0) return fail(ctx, "blurRad must be a positive, non-zero integer");   // init.lua:586-587
+  if (src->data == dst->data) return fail(ctx, "rectangularBlur: dst must not alias src");
+  const size_t cells = (size_t)src->nb * src->nc * src->nz * src->ny * src->nx;
+  if (arena_reserve(ctx, carve_bytes({cells * 4}))) return 1;
+  Carver cv(ctx);
+  float* tmp = cv.take<float>(cells);
+  const int nbf = src->nb * src->nc;
+  cudaStream_t st = ctx->stream;
+  // generic/tfluids.cc:700-757: z into dst (3-D), y into tmp, x into dst.
+  const float* cur = src->data;
+  if (is_3d) {
+    launch_blur_axis(cur, dst->data, nbf, src->nz, src->ny, src->nx, 2, blur_rad, st);
+    cur = dst->data;
+    ctx->launches += 1;
+  }
+  launch_blur_axis(cur, tmp, nbf, src->nz, src->ny, src->nx, 1, blur_rad, st);
+  launch_blur_axis(tmp, dst->data, nbf, src->nz, src->ny, src->nx, 0, blur_rad, st);
+  ctx->launches += 2;
+  return check_launch(ctx, "rectangularBlur");
+}
+
+int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_rad, int is_3d, const tfl_grid* dst) {
+  if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, dst, "dst")) return 1;
+  if (!same_spatial(flags, dst)) return fail(ctx, "size mismatch");
+  if (search_rad <= 0) return fail(ctx, "searchRad must be a positive, non-zero integer");   // init.lua:609-610
+  if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
+  launch_signed_distance_field(flags->data, dst->data, flags->nb, flags->nz, flags->ny, flags->nx, search_rad,
+                               ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "signedDistanceField");
+}
+
 // Debug hook (not in include/tfl.h): planes per CTA of the PCG sweep pipeline.
 extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
   if (!ctx) return 1;

@@ -94,5 +94,14 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
               int nx, int is3d, int precond, float tol, int max_iter, float* residual, int* iterations,
               long long* launches, cudaStream_t st);
 void pcg_release(PcgScratch& sc);
+int normalize_pressure_mean(void* workspace, float* p, const float* flags, int nb, int nz, int ny, int nx, int is3d,
+                            long long* launches, cudaStream_t st);
+
+// ---- tfl_aux_ops.cu (-fmad=false): operators of tfluids/init.lua around the step ----
+void launch_upsample_nearest(const float* in, float* out, int nbf, int nz, int ny, int nx, int ratio, cudaStream_t st);
+// axis: 0 = x, 1 = y, 2 = z of a [nbf][nz][ny][nx] array.
+void launch_blur_axis(const float* src, float* dst, int nbf, int nz, int ny, int nx, int axis, int rad, cudaStream_t st);
+void launch_signed_distance_field(const float* flags, float* dst, int nb, int nz, int ny, int nx, int rad,
+                                  cudaStream_t st);
 
 }  // namespace tfl

@@ -84,13 +84,22 @@ __global__ void k_label_init(const float* __restrict__ flags, int* __restrict__ 
     if (border) atomicOr(status, 1);          // generic/tfluids.cu:1083-1090 raises
   }
 }
+// SAFE: fluid cells may sit on the domain border (normalizePressureMean accepts any flag grid), so the
+// backward neighbours are bounds-checked; the PCG path has already rejected such grids.
+template <bool SAFE>
 __global__ void k_label_union(int* __restrict__ parent, PcgGeo g, const int* __restrict__ status) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.n * g.nb || *status) return;
+  if (c >= g.n * g.nb || (!SAFE && *status)) return;
   if (parent[c] < 0) return;
-  if (parent[c - 1] >= 0) unite(parent, (int)c, (int)c - 1);
-  if (parent[c - g.nx] >= 0) unite(parent, (int)c, (int)c - g.nx);
-  if (g.is3d && parent[c - (long long)g.nx * g.ny] >= 0) unite(parent, (int)c, (int)(c - (long long)g.nx * g.ny));
+  bool xm = true, ym = true, zm = g.is3d != 0;
+  if (SAFE) {
+    const long long cc = c % g.n;
+    const int i = (int)(cc % g.nx), j = (int)((cc / g.nx) % g.ny), k = (int)(cc / ((long long)g.nx * g.ny));
+    xm = i > 0; ym = j > 0; zm = zm && k > 0;
+  }
+  if (xm && parent[c - 1] >= 0) unite(parent, (int)c, (int)c - 1);
+  if (ym && parent[c - g.nx] >= 0) unite(parent, (int)c, (int)c - g.nx);
+  if (zm && parent[c - (long long)g.nx * g.ny] >= 0) unite(parent, (int)c, (int)(c - (long long)g.nx * g.ny));
 }
 __global__ void k_label_flatten(int* __restrict__ parent, int* __restrict__ csize, PcgGeo g) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -564,6 +573,26 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
   if (!is_aux) warp_comp_add(a.rz, racc.comp, racc.v);
 }
 
+// ---- normalizePressureMean (generic/tfluids.cc:845-921) -----------------------------------------
+__global__ void k_npm_sum(const float* __restrict__ p, const int* __restrict__ parent, double* __restrict__ sums,
+                          long long cells) {
+  CompAcc a;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+    const int root = parent[c];
+    if (root >= 0) a.add(sums, root, (double)p[c]);
+  }
+  warp_comp_add(sums, a.comp, a.v);
+}
+__global__ void k_npm_subtract(float* __restrict__ p, const int* __restrict__ parent, const int* __restrict__ csize,
+                               const double* __restrict__ sums, long long cells) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cells) return;
+  const int root = parent[c];
+  if (root < 0) return;
+  const float mean = (float)sums[root] / (float)csize[root];
+  p[c] = p[c] - mean;
+}
+
 inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -636,7 +665,7 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   PCG_CUDA(cudaMemsetAsync(header, 0, 64, st));
   PCG_CUDA(cudaMemsetAsync(csize, 0, cells * 4, st));
   k_label_init<<<blocks_for(cells), 256, 0, st>>>(flags, parent, g, header + 4);
-  k_label_union<<<blocks_for(cells), 256, 0, st>>>(parent, g, header + 4);
+  k_label_union<false><<<blocks_for(cells), 256, 0, st>>>(parent, g, header + 4);
   k_label_flatten<<<blocks_for(cells), 256, 0, st>>>(parent, csize, g);
   k_label_assign<<<blocks_for(cells), 256, 0, st>>>(parent, csize, cid, g, header + 3);
   *launches += 4;
@@ -750,6 +779,38 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   if (iterations) *iterations = worst_it;
   return 0;
 #undef PCG_CUDA
+}
+
+// p -= mean of p over the cell's connected fluid component, every component of every batch element.
+// The reference copies p and flags to the host, flood-fills there and copies back (init.lua:747-765).
+int normalize_pressure_mean(void* workspace, float* p, const float* flags, int nb, int nz, int ny, int nx, int is3d,
+                            long long* launches, cudaStream_t st) {
+  PcgGeo g;
+  g.nx = nx; g.ny = ny; g.nz = nz; g.nb = nb; g.is3d = is3d ? 1 : 0;
+  g.n = (long long)nz * ny * nx;
+  g.S = 0; g.NYP = 0; g.P = nb * nz; g.plane = 0; g.slots = 0; g.GP = 1; g.chunks = 0;
+  const long long cells = g.n * nb;
+  char* base = (char*)workspace;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; char* r_ = base + off; off += bytes; return r_; };
+  int* parent = (int*)take(cells * 4);
+  int* csize = (int*)take(cells * 4);
+  double* sums = (double*)take(cells * 8);
+  int* status = (int*)take(64);
+  if (cudaMemsetAsync(csize, 0, cells * 4, st) != cudaSuccess) return 3;
+  if (cudaMemsetAsync(sums, 0, cells * 8, st) != cudaSuccess) return 3;
+  if (cudaMemsetAsync(status, 0, 64, st) != cudaSuccess) return 3;
+  k_label_init<<<blocks_for(cells), 256, 0, st>>>(flags, parent, g, status);
+  k_label_union<true><<<blocks_for(cells), 256, 0, st>>>(parent, g, status);
+  k_label_flatten<<<blocks_for(cells), 256, 0, st>>>(parent, csize, g);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned blocks = (unsigned)std::min<long long>((cells + 255) / 256, (long long)sms * 8);
+  k_npm_sum<<<blocks, 256, 0, st>>>(p, parent, sums, cells);
+  k_npm_subtract<<<blocks_for(cells), 256, 0, st>>>(p, parent, csize, sums, cells);
+  *launches += 5;
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 
 void pcg_release(PcgScratch& sc) {

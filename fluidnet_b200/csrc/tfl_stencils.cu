@@ -412,9 +412,12 @@ __global__ void k_advect_scalar_pass2_manta(const float* __restrict__ s, const f
       if (g.is3d) inb = inb && k0 >= 0 && k1 < g.gnz; else inb = inb && k0 == 0 && k1 == 0;
       if (!inb) { bail = true; break; }
       const int kl0 = local_z(g, k0), kl1 = g.is3d ? local_z(g, k1) : kl0;
-#define TFL_MM(kk, jj, ii) { const float t = __ldg(sb + cell(g, kk, jj, ii)); if (t < lo) lo = t; if (t > hi) hi = t; }
-      TFL_MM(kl0, j0, i0) TFL_MM(kl0, j0, i1) TFL_MM(kl0, j1, i0) TFL_MM(kl0, j1, i1)
-      if (g.is3d) { TFL_MM(kl1, j0, i0) TFL_MM(kl1, j0, i1) TFL_MM(kl1, j1, i0) TFL_MM(kl1, j1, i1) }
+// The eight corners sit at fixed offsets from the first one (same visiting order as the reference).
+      const float* a0 = sb + cell(g, kl0, j0, i0);
+      const int dzo = (kl1 - kl0) * g.ny * g.nx;
+#define TFL_MM(off) { const float t = __ldg(a0 + (off)); if (t < lo) lo = t; if (t > hi) hi = t; }
+      TFL_MM(0) TFL_MM(1) TFL_MM(g.nx) TFL_MM(g.nx + 1)
+      if (g.is3d) { TFL_MM(dzo) TFL_MM(dzo + 1) TFL_MM(dzo + g.nx) TFL_MM(dzo + g.nx + 1) }
 #undef TFL_MM
     }
     v = bail ? fw : clamp_f(v, lo, hi);
@@ -434,8 +437,10 @@ __global__ void k_advect_scalar_pass2_manta(const float* __restrict__ s, const f
 // ---------------------------------------------------------------------------------------
 // advectVel
 // ---------------------------------------------------------------------------------------
+// vel[c]: velocity at the centre of face c of this cell (mac_at_x/y/z of the advecting field), computed
+// by the caller because the MacCormack clamp of the same cell needs the same three vectors.
 template <bool OURS, typename FT>
-__device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const float* __restrict__ ub,
+__device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const V3 (&vel)[3],
                                               const float* __restrict__ src, const Geo& g, float dt, int k,
                                               int j, int i) {
   V3 r;
@@ -447,25 +452,25 @@ __device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const f
   const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
   V3 p;
   if (OURS) {
-    line_trace(fl, g, start, scale3(mac_at_x(ub, g, k, j, i), -dt), &p);
+    line_trace(fl, g, start, scale3(vel[0], -dt), &p);
     r.x = lerp_block(src, g, p);
-    line_trace(fl, g, start, scale3(mac_at_y(ub, g, k, j, i), -dt), &p);
+    line_trace(fl, g, start, scale3(vel[1], -dt), &p);
     r.y = lerp_block(src + g.n, g, p);
     if (g.is3d) {
-      line_trace(fl, g, start, scale3(mac_at_z(ub, g, k, j, i), -dt), &p);
+      line_trace(fl, g, start, scale3(vel[2], -dt), &p);
       r.z = lerp_block(src + 2 * g.n, g, p);
     } else {
       r.z = 0.0f;
     }
   } else {
-    V3 v = scale3(mac_at_x(ub, g, k, j, i), dt);
+    V3 v = scale3(vel[0], dt);
     p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
     r.x = lerp_block(src, g, p);
-    v = scale3(mac_at_y(ub, g, k, j, i), dt);
+    v = scale3(vel[1], dt);
     p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
     r.y = lerp_block(src + g.n, g, p);
     if (g.is3d) {
-      v = scale3(mac_at_z(ub, g, k, j, i), dt);
+      v = scale3(vel[2], dt);
       p = V3{start.x - v.x, start.y - v.y, start.z - v.z};
       r.z = lerp_block(src + 2 * g.n, g, p);
     } else {
@@ -473,6 +478,12 @@ __device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const f
     }
   }
   return r;
+}
+__device__ __forceinline__ void mac_face_velocities(const float* __restrict__ ub, const Geo& g, int k, int j, int i,
+                                                    V3 (&vel)[3]) {
+  vel[0] = mac_at_x(ub, g, k, j, i);
+  vel[1] = mac_at_y(ub, g, k, j, i);
+  vel[2] = g.is3d ? mac_at_z(ub, g, k, j, i) : V3{0.0f, 0.0f, 0.0f};
 }
 
 // Resident CTAs per SM the advectVel kernels are compiled for (register budget 65536 / 256 / N).
@@ -492,7 +503,11 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB1) k_advect_vel_pass1(cons
   const int c = cell(g, k, j, i);
   const float* ub = U + (long long)b * g.nc * g.n;
   V3 v = {0.0f, 0.0f, 0.0f};
-  if (!on_border(g, k, j, i)) v = advect_mac_cell<OURS>(flags + b * g.n, ub, ub, g, dt, k, j, i);
+  if (!on_border(g, k, j, i)) {
+    V3 vel[3];
+    mac_face_velocities(ub, g, k, j, i, vel);
+    v = advect_mac_cell<OURS>(flags + b * g.n, vel, ub, g, dt, k, j, i);
+  }
   float* ob = out + (long long)b * g.nc * g.n + c;
   ob[0] = v.x; ob[g.n] = v.y;
   if (g.is3d) ob[2 * g.n] = v.z;
@@ -513,9 +528,12 @@ __device__ __forceinline__ float clamp_component_mac(const float* __restrict__ o
     if (g.is3d) inb = inb && k0 >= 0 && k1 < g.gnz; else inb = inb && k0 == 0 && k1 == 0;
     if (!inb) return fwd;
     const int kl0 = local_z(g, k0), kl1 = g.is3d ? local_z(g, k1) : kl0;
-#define TFL_MM(kk, jj, ii) { const float t = __ldg(orig_c + cell(g, kk, jj, ii)); if (t < lo) lo = t; if (t > hi) hi = t; }
-    TFL_MM(kl0, j0, i0) TFL_MM(kl0, j0, i1) TFL_MM(kl0, j1, i0) TFL_MM(kl0, j1, i1)
-    if (g.is3d) { TFL_MM(kl1, j0, i0) TFL_MM(kl1, j0, i1) TFL_MM(kl1, j1, i0) TFL_MM(kl1, j1, i1) }
+// The eight corners sit at fixed offsets from the first one (same visiting order as the reference).
+    const float* a0 = orig_c + cell(g, kl0, j0, i0);
+    const int dzo = (kl1 - kl0) * g.ny * g.nx;
+#define TFL_MM(off) { const float t = __ldg(a0 + (off)); if (t < lo) lo = t; if (t > hi) hi = t; }
+    TFL_MM(0) TFL_MM(1) TFL_MM(g.nx) TFL_MM(g.nx + 1)
+    if (g.is3d) { TFL_MM(dzo) TFL_MM(dzo + 1) TFL_MM(dzo + g.nx) TFL_MM(dzo + g.nx + 1) }
 #undef TFL_MM
   }
   return clamp_f(val, lo, hi);
@@ -536,7 +554,11 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(cons
   const float* fb = fwd + (long long)b * g.nc * g.n;
   const bool border = on_border(g, k, j, i);
   V3 bw = {0.0f, 0.0f, 0.0f};
-  if (!border) bw = advect_mac_cell<OURS>(fl, ub, fb, g, -dt, k, j, i);
+  V3 vel[3];
+  if (!border) {
+    mac_face_velocities(ub, g, k, j, i, vel);
+    bw = advect_mac_cell<OURS>(fl, vel, fb, g, -dt, k, j, i);
+  }
   const int kg = k + g.zoff;
   const bool cf = flag_i(fl, g, k, j, i) & kFluid;
   bool skip[3] = {!cf, !cf, !cf};
@@ -555,11 +577,11 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(cons
     val[a] = v;
   }
   if (!border) {
-    val[0] = clamp_component_mac(ub, g, val[0], fwv[0], kg, j, i, scale3(mac_at_x(ub, g, k, j, i), dt));
-    val[1] = clamp_component_mac(ub + g.n, g, val[1], fwv[1], kg, j, i, scale3(mac_at_y(ub, g, k, j, i), dt));
+    val[0] = clamp_component_mac(ub, g, val[0], fwv[0], kg, j, i, scale3(vel[0], dt));
+    val[1] = clamp_component_mac(ub + g.n, g, val[1], fwv[1], kg, j, i, scale3(vel[1], dt));
     if (g.is3d)
       val[2] = clamp_component_mac(ub + 2 * g.n, g, val[2], fwv[2], kg, j, i,
-                                   scale3(mac_at_z(ub, g, k, j, i), dt));
+                                   scale3(vel[2], dt));
   }
   float* db = dst + (long long)b * g.nc * g.n + c;
   for (int a = 0; a < g.nc; a++) db[a * g.n] = val[a];

@@ -54,6 +54,10 @@ int tfl_solve_linear_system_jacobi(tfl_ctx*, const tfl_grid* p, const tfl_grid* 
 int tfl_precond_from_string(const char* name);
 int tfl_solve_linear_system_pcg(tfl_ctx*, const tfl_grid* p, const tfl_grid* flags, const tfl_grid* div,
                                 int is_3d, int precond, float tol, int max_iter, float* residual, int* iterations);
+int tfl_normalize_pressure_mean(tfl_ctx*, const tfl_grid* p, const tfl_grid* flags, int is_3d);
+int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx*, int ratio, const tfl_grid* input, const tfl_grid* output);
+int tfl_rectangular_blur(tfl_ctx*, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst);
+int tfl_signed_distance_field(tfl_ctx*, const tfl_grid* flags, int search_rad, int is_3d, const tfl_grid* dst);
 int tfl_empty_domain(tfl_ctx*, const tfl_grid* flags, int is_3d, int bnd);
 int tfl_flags_to_occupancy(tfl_ctx*, const tfl_grid* flags, const tfl_grid* occupancy, int64_t* bad_cells);
 int tfl_apply_bc(tfl_ctx*, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc);
@@ -208,6 +212,21 @@ function tfluids.solveLinearSystemPCG(p, flags, div, is3D, tol, maxIter, precond
   local res = ffi.new('float[1]')
   check(lib.tfl_solve_linear_system_pcg(ctx, p.c, flags.c, div.c, is3D and 1 or 0, kind, tol, maxIter, res, nil))
   return res[0]
+end
+
+function tfluids.normalizePressureMean(p, flags, is3D)                      -- init.lua:747-765 (no host round trip)
+  check(lib.tfl_normalize_pressure_mean(ctx, p.c, flags.c, is3D and 1 or 0))
+end
+function tfluids.volumetricUpSamplingNearestForward(ratio, input, output)  -- init.lua:618-622
+  check(lib.tfl_volumetric_up_sampling_nearest_forward(ctx, ratio, input.c, output.c))
+end
+function tfluids.rectangularBlur(src, blurRad, is3D, dst)                  -- init.lua:583-596
+  assert(blurRad > 0 and math.floor(blurRad) == blurRad, 'blurRad must be a positive, non-zero integer')
+  check(lib.tfl_rectangular_blur(ctx, src.c, blurRad, is3D and 1 or 0, dst.c))
+end
+function tfluids.signedDistanceField(flags, searchRad, is3D, dst)          -- init.lua:604-614
+  assert(searchRad > 0 and math.floor(searchRad) == searchRad, 'searchRad must be a positive, non-zero integer')
+  check(lib.tfl_signed_distance_field(ctx, flags.c, searchRad, is3D and 1 or 0, dst.c))
 end
 
 -- The cutorch pair inside setConstVals (lib/simulate.lua:136-158) and U:clamp (:326).

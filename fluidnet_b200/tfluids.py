@@ -299,6 +299,44 @@ def solveLinearSystemPCG(p, flags, div, is3D, tol=None, maxIter=None, precondTyp
     return float(res.value)
 
 
+def normalizePressureMean(p, flags, is3D):
+    """init.lua:747-765: remove the mean of p over every connected fluid component (on the device;
+    the reference round-trips through the host)."""
+    assert p.dim() == 5 and flags.dim() == 5 and p.size() == flags.size()
+    assert p.is_contiguous() and flags.is_contiguous()
+    c = _ctx_for(p)
+    c.check(c.lib.tfl_normalize_pressure_mean(c.h, _grid(p), _grid(flags), 1 if is3D else 0))
+
+
+def volumetricUpSamplingNearestForward(ratio, input, output):
+    """init.lua:618-622."""
+    assert input.dim() == 5 and output.dim() == 5, 'ERROR: input and output must be dim 5'
+    assert input.is_contiguous() and output.is_contiguous()
+    c = _ctx_for(input)
+    c.check(c.lib.tfl_volumetric_up_sampling_nearest_forward(c.h, int(ratio), _grid(input), _grid(output)))
+
+
+def rectangularBlur(src, blurRad, is3D, dst):
+    """init.lua:583-596."""
+    assert src.dim() == 5 and dst.dim() == 5
+    assert src.size() == dst.size()
+    assert blurRad > 0 and int(blurRad) == blurRad, 'blurRad must be a positive, non-zero integer'
+    assert src.is_contiguous() and dst.is_contiguous()
+    c = _ctx_for(src)
+    c.check(c.lib.tfl_rectangular_blur(c.h, _grid(src), int(blurRad), 1 if is3D else 0, _grid(dst)))
+
+
+def signedDistanceField(flags, searchRad, is3D, dst):
+    """init.lua:604-614."""
+    assert flags.dim() == 5 and dst.dim() == 5
+    assert flags.size() == dst.size()
+    assert flags.is_contiguous() and dst.is_contiguous()
+    assert flags.size(1) == 1, 'flags must be scalar'
+    assert searchRad > 0 and int(searchRad) == searchRad, 'searchRad must be a positive, non-zero integer'
+    c = _ctx_for(flags)
+    c.check(c.lib.tfl_signed_distance_field(c.h, _grid(flags), int(searchRad), 1 if is3D else 0, _grid(dst)))
+
+
 def applyBC(x, invMask, bc):
     """x:cmul(invMask); x:add(bc) -- the cutorch pair in setConstVals (lib/simulate.lua:136-158)."""
     c = _ctx_for(x)

@@ -142,6 +142,23 @@ int tfl_precond_from_string(const char* name);   /* "none" | "ilu0" | "ic0"; -1 
 int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
                                 const tfl_grid* div, int is_3d, int precond, float tol, int max_iter,
                                 float* residual, int* iterations);
+
+/* ---- operators of tfluids/init.lua around the step --------------------------------------- */
+/* tfluids.normalizePressureMean (init.lua:747-765; generic/tfluids.cc:845-921): subtract from every
+ * fluid cell the mean of p over its connected fluid component.  The reference round-trips through the
+ * host for the flood fill; here the labelling runs on the device. */
+int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, int is_3d);
+/* tfluids.volumetricUpSamplingNearestForward (init.lua:618-622; generic/tfluids.cc:509-557):
+ * output [b][f][z*r][y*r][x*r] = input [b][f][z][y][x] replicated. */
+int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tfl_grid* input,
+                                               const tfl_grid* output);
+/* tfluids.rectangularBlur (init.lua:583-596; generic/tfluids.cc:641-760): separable box blur of
+ * radius blur_rad with clamped edges, z (3-D only) then y then x; dst may not alias src. */
+int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst);
+/* tfluids.signedDistanceField (init.lua:604-614; generic/tfluids.cc:766-822): 0 in obstacle cells,
+ * else the distance to the nearest obstacle cell within search_rad, capped at search_rad. */
+int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_rad, int is_3d,
+                              const tfl_grid* dst);
 /* tfluids.emptyDomain (init.lua:545-555; generic/tfluids.cu:314-353). */
 int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd);
 /* tfluids.flagsToOccupancy (init.lua:571-576; generic/tfluids.cu:355-401).  Cells that are

@@ -216,6 +216,37 @@ class Oracle:
                                          C.c_int(sizes.size))
         return comp, sizes[:n].copy()
 
+    # -- operators of tfluids/init.lua around the step ("next" rows) ----------------------------
+    def volumetricUpSamplingNearestForward(self, ratio, x):
+        x = _f32(x)
+        nb, nf, nz, ny, nx = x.shape
+        out = np.empty((nb, nf, nz * ratio, ny * ratio, nx * ratio), np.float32)
+        self.lib.orc_upsample_nearest(_ptr(x), _ptr(out), C.c_int(nb), C.c_int(nf), C.c_int(nz), C.c_int(ny),
+                                      C.c_int(nx), C.c_int(ratio))
+        return out
+
+    def rectangularBlur(self, src, blurRad, is3D):
+        src = _f32(src)
+        dst, tmp = np.empty_like(src), np.empty_like(src)
+        nb, nf, nz, ny, nx = src.shape
+        self.lib.orc_rectangular_blur(_ptr(src), C.c_int(blurRad), C.c_int(1 if is3D else 0), _ptr(dst), _ptr(tmp),
+                                      C.c_int(nb), C.c_int(nf), C.c_int(nz), C.c_int(ny), C.c_int(nx))
+        return dst
+
+    def signedDistanceField(self, flags, searchRad, is3D):
+        flags = _f32(flags)
+        d = _dims(flags, is3D)
+        dst = np.empty_like(flags)
+        self.lib.orc_signed_distance_field(_ptr(flags), C.c_int(searchRad), _ptr(dst), C.byref(d))
+        return dst
+
+    def normalizePressureMean(self, p, flags, is3D):
+        assert p.dtype == np.float32 and p.flags.c_contiguous
+        flags = _f32(flags)
+        d = _dims(flags, is3D)
+        self.lib.orc_normalize_pressure_mean(_ptr(p), _ptr(flags), C.byref(d))
+        return p
+
     def calcLineTrace(self, pos, delta, flags, is3D=True):
         flags = _f32(flags)
         d = _dims(flags, is3D)
@@ -395,6 +426,30 @@ class Reference(Oracle):
             raise RuntimeError("reference calcLineTrace: " + err.value.decode())
         return bool(hit), out
 
+
+    def volumetricUpSamplingNearestForward(self, ratio, x):
+        x = _f32(x)
+        nb, nf, nz, ny, nx = x.shape
+        out = np.empty((nb, nf, nz * ratio, ny * ratio, nx * ratio), np.float32)
+        self._call("volumetricUpSamplingNearestForward", ratio, x, out)
+        return out
+
+    def rectangularBlur(self, src, blurRad, is3D):
+        src = _f32(src)
+        dst, tmp = np.empty_like(src), np.empty_like(src)
+        self._call("rectangularBlur", src, blurRad, is3D, dst, tmp)
+        return dst
+
+    def signedDistanceField(self, flags, searchRad, is3D):
+        flags = _f32(flags)
+        dst = np.empty_like(flags)
+        self._call("signedDistanceField", flags, searchRad, is3D, dst)
+        return dst
+
+    def normalizePressureMean(self, p, flags, is3D):
+        inds = np.zeros(p.shape[:1] + p.shape[2:], np.int32)
+        self._call("normalizePressureMean", p, _f32(flags), is3D, inds)
+        return p
 
     def findConnectedFluidComponents(self, flags, is3D, ibatch=0):
         flags = _f32(flags).copy()

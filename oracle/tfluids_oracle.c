@@ -1162,6 +1162,104 @@ int orc_pcg(float* p, const float* flags, const float* div, const orc_dims* d, i
 }
 
 /* ------------------------------------------------------------------------------------
+ * Operators of tfluids/init.lua around the step ("next" rows of the scope table): all four have
+ * CPU code in the reference (generic/tfluids.cc), so the restatements below are pinned bit-exactly
+ * (the mean removal: to float rounding, its accumulation order is an OpenMP atomic).
+ * ---------------------------------------------------------------------------------- */
+/* volumetricUpSamplingNearestForward, generic/tfluids.cc:509-557: out[z][y][x] = in[z/r][y/r][x/r].
+ * in: [nb][nf][nz][ny][nx], out: [nb][nf][nz*r][ny*r][nx*r]. */
+void orc_upsample_nearest(const float* in, float* out, int nb, int nf, int nz, int ny, int nx, int ratio) {
+  const long oz = (long)nz * ratio, oy = (long)ny * ratio, ox = (long)nx * ratio;
+  long bf;
+#pragma omp parallel for schedule(static)
+  for (bf = 0; bf < (long)nb * nf; bf++)
+    for (long z = 0; z < oz; z++) for (long y = 0; y < oy; y++) for (long x = 0; x < ox; x++)
+      out[((bf * oz + z) * oy + y) * ox + x] = in[((bf * nz + z / ratio) * ny + y / ratio) * nx + x / ratio];
+}
+
+/* DoRectangularBlurAlongAxis, generic/tfluids.cc:641-668: running box sum with clamped edges. */
+static void blur_axis(const float* src, int size, long stride, int rad, float* dst) {
+  float val = src[0] * (float)(rad + 1);
+  for (int i = 0; i < size && i < rad; i++) val += src[i * stride];
+  const float mul_const = 1.0f / (float)(rad * 2 + 1);
+  for (int i = 0; i < size; i++) {
+    const int iminus = i - rad - 1 > 0 ? i - rad - 1 : 0;
+    val -= src[iminus * stride];
+    const int iplus = i + rad < size - 1 ? i + rad : size - 1;
+    val += src[iplus * stride];
+    dst[i * stride] = val * mul_const;
+  }
+}
+/* rectangularBlur, generic/tfluids.cc:670-760: z (3-D only), then y, then x; tmp is scratch. */
+void orc_rectangular_blur(const float* src, int rad, int is3d, float* dst, float* tmp, int nb, int nf, int nz,
+                          int ny, int nx) {
+  const long sy = nx, sz = (long)nx * ny, sf = sz * nz;
+  const float* cur_src = src;
+  float* cur_dst = is3d ? dst : tmp;
+  long bf;
+  if (is3d) {
+#pragma omp parallel for schedule(static)
+    for (bf = 0; bf < (long)nb * nf; bf++)
+      for (long y = 0; y < ny; y++) for (long x = 0; x < nx; x++)
+        blur_axis(cur_src + bf * sf + y * sy + x, nz, sz, rad, cur_dst + bf * sf + y * sy + x);
+    cur_src = dst;
+    cur_dst = tmp;
+  }
+#pragma omp parallel for schedule(static)
+  for (bf = 0; bf < (long)nb * nf; bf++)
+    for (long z = 0; z < nz; z++) for (long x = 0; x < nx; x++)
+      blur_axis(cur_src + bf * sf + z * sz + x, ny, sy, rad, cur_dst + bf * sf + z * sz + x);
+  cur_src = tmp;
+  cur_dst = dst;
+#pragma omp parallel for schedule(static)
+  for (bf = 0; bf < (long)nb * nf; bf++)
+    for (long z = 0; z < nz; z++) for (long y = 0; y < ny; y++)
+      blur_axis(cur_src + bf * sf + z * sz + y * sy, nx, 1, rad, cur_dst + bf * sf + z * sz + y * sy);
+}
+
+/* signedDistanceField, generic/tfluids.cc:766-822: 0 in obstacles, else the distance to the nearest
+ * obstacle cell inside a (2 r + 1)^3 window, capped at r. */
+void orc_signed_distance_field(const float* flags, int search_rad, float* dst, const orc_dims* d) {
+  const long n = cells(d);
+  long bc;
+#pragma omp parallel for schedule(static)
+  for (bc = 0; bc < n * d->nb; bc++) {
+    const int b = (int)(bc / n);
+    const long c = bc % n;
+    const int x = (int)(c % d->nx), y = (int)((c / d->nx) % d->ny), z = (int)(c / ((long)d->nx * d->ny));
+    if (is_obstacle(flags, d, b, z, y, x)) { dst[bc] = 0.0f; continue; }
+    float dist_sq = (float)(search_rad * search_rad);
+    const int zmin = z - search_rad > 0 ? z - search_rad : 0, zmax = z + search_rad < d->nz - 1 ? z + search_rad : d->nz - 1;
+    const int ymin = y - search_rad > 0 ? y - search_rad : 0, ymax = y + search_rad < d->ny - 1 ? y + search_rad : d->ny - 1;
+    const int xmin = x - search_rad > 0 ? x - search_rad : 0, xmax = x + search_rad < d->nx - 1 ? x + search_rad : d->nx - 1;
+    for (int zs = zmin; zs <= zmax; zs++) for (int ys = ymin; ys <= ymax; ys++) for (int xs = xmin; xs <= xmax; xs++)
+      if (is_obstacle(flags, d, b, zs, ys, xs)) {
+        const float cur = (float)((z - zs) * (z - zs) + (y - ys) * (y - ys) + (x - xs) * (x - xs));
+        if (dist_sq > cur) dist_sq = cur;
+      }
+    dst[bc] = sqrtf(dist_sq);
+  }
+}
+
+/* normalizePressureMean, generic/tfluids.cc:845-921: subtract from every fluid cell the mean of p over
+ * its connected fluid component (components of one cell included). */
+void orc_normalize_pressure_mean(float* p, const float* flags, const orc_dims* d) {
+  const long n = cells(d);
+  int* comp = (int*)malloc(sizeof(int) * (size_t)n);
+  int* sizes = (int*)malloc(sizeof(int) * (size_t)(n + 1));
+  for (int b = 0; b < d->nb; b++) {
+    const int nc = orc_find_components(flags, d, b, comp, sizes, (int)n);
+    float* mean = (float*)calloc((size_t)(nc > 0 ? nc : 1), sizeof(float));
+    for (long c = 0; c < n; c++) if (comp[c] >= 0) mean[comp[c]] += p[(long)b * n + c];
+    for (int q = 0; q < nc; q++) mean[q] = mean[q] / (float)sizes[q];
+    for (long c = 0; c < n; c++) if (comp[c] >= 0) p[(long)b * n + c] = p[(long)b * n + c] - mean[comp[c]];
+    free(mean);
+  }
+  free(comp);
+  free(sizes);
+}
+
+/* ------------------------------------------------------------------------------------
  * Lua-side pieces of the loop (lib/simulate.lua).
  * ---------------------------------------------------------------------------------- */
 /* x = x * invMask + bc  (setConstVals, lib/simulate.lua:136-158: cmul then add). */
