@@ -195,6 +195,368 @@ __global__ void k_cnn_finish_fused(const float* __restrict__ p_net, float* __res
   p_out[b * g.n + c] = pc * sc;
 }
 
+// ---------------------------------------------------------------------------------------
+// Four voxels along x per thread (rows with nx % 4 == 0): the same per-voxel arithmetic as the
+// kernels above, in the same order, behind 16-byte loads / stores and one flag word per row --
+// these stages are bound by instruction issue and load latency, not by HBM bandwidth, so fewer,
+// wider memory instructions and fewer index computations per voxel are what pays.
+// ---------------------------------------------------------------------------------------
+struct Flags4 { int c[4]; };
+__device__ __forceinline__ Flags4 flags4(const unsigned char* __restrict__ p, bool valid) {
+  Flags4 f;
+  if (valid) {
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(p));
+    f.c[0] = v.x; f.c[1] = v.y; f.c[2] = v.z; f.c[3] = v.w;
+  } else {
+    f.c[0] = f.c[1] = f.c[2] = f.c[3] = 0;
+  }
+  return f;
+}
+__device__ __forceinline__ void ld4(const float* __restrict__ p, float (&o)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void ld4_rw(const float* p, float (&o)[4]) {      // data this kernel also writes
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void zero4(float (&o)[4]) { o[0] = o[1] = o[2] = o[3] = 0.0f; }
+
+// wall_bc_zero_mask (tfl_device.cuh) on flag values; a neighbour outside the grid is passed as 0.
+__device__ __forceinline__ void wall_mask_from_flags(int fc, int fxm, int fxp, int fym, int fyp, int fzm, int fzp,
+                                                     bool is3d, bool z[3]) {
+  z[0] = z[1] = z[2] = false;
+  const bool cf = fc & kFluid, co = fc & kObstacle;
+  if (!cf && !co) return;
+  if ((fxm & kObstacle) || (co && (fxm & kFluid))) z[0] = true;
+  if ((fym & kObstacle) || (co && (fym & kFluid))) z[1] = true;
+  if ((fzm & kObstacle) || (co && (fzm & kFluid))) z[2] = true;
+  if (cf) {
+    if ((fxm & kStick) || (fxp & kStick)) { z[1] = true; if (is3d) z[2] = true; }
+    if ((fym & kStick) || (fyp & kStick)) { z[0] = true; if (is3d) z[2] = true; }
+    if (is3d && ((fzm & kStick) || (fzp & kStick))) { z[0] = true; z[1] = true; }
+  }
+}
+
+// (b, k, j, i0 .. i0 + 3) of this thread.  The fused step never runs on a slab (zlo = 0, zhi = nz).
+__device__ __forceinline__ bool thread_cell4(const Geo& g, int& b, int& k, int& j, int& i0) {
+  i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int zz = blockIdx.z * blockDim.z + threadIdx.z;
+  b = zz / g.nz;
+  k = zz - b * g.nz;
+  return i0 < g.nx && j < g.ny && b < g.nb;
+}
+
+// The flag values around a quad: centre row, the scalars left / right of it, and the four rows around.
+struct QuadFlags {
+  Flags4 c, ym, yp, zm, zp;
+  int left, right;
+  __device__ __forceinline__ int xm(int v) const { return v == 0 ? left : c.c[v - 1]; }
+  __device__ __forceinline__ int xp(int v) const { return v == 3 ? right : c.c[v + 1]; }
+};
+template <bool IS3D>
+__device__ __forceinline__ QuadFlags quad_flags(const unsigned char* __restrict__ fl, const Geo& g, int c0, int k, int j,
+                                                int i0, bool need_plus) {
+  QuadFlags q;
+  const int sy = g.nx, sz = g.nx * g.ny;
+  q.c = flags4(fl + c0, true);
+  q.left = i0 > 0 ? (int)__ldg(fl + c0 - 1) : 0;
+  q.ym = flags4(fl + c0 - sy, j > 0);
+  q.zm = flags4(fl + c0 - sz, IS3D && k > 0);
+  q.right = (need_plus && i0 + 4 < g.nx) ? (int)__ldg(fl + c0 + 4) : 0;
+  q.yp = flags4(fl + c0 + sy, need_plus && j < g.ny - 1);
+  q.zp = flags4(fl + c0 + sz, need_plus && IS3D && k < g.nz - 1);
+  return q;
+}
+
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ tmp_s, const float* __restrict__ tmp_u,
+                                                      const unsigned char* __restrict__ flags, float* __restrict__ density,
+                                                      float* __restrict__ U, BcPtrs bc, int do_buoy, float sx, float sy_,
+                                                      float sz_, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const int c0 = cell(g, k, j, i0);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const long long sb = b * g.n, ub = (long long)b * g.nc * g.n;
+  float rc[4];
+  zero4(rc);
+  auto dens_bc = [&](long long o, float (&out)[4]) {          // BC(tmp_s) of the quad at offset o
+    ld4(tmp_s + o, out);
+    if (bc.d_inv) {
+      float iv[4], bv[4];
+      ld4(bc.d_inv + o, iv);
+      ld4(bc.d_bc + o, bv);
+#pragma unroll
+      for (int v = 0; v < 4; v++) { const float t = out[v] * iv[v]; out[v] = t + bv[v]; }
+    }
+  };
+  if (density) {
+    dens_bc(sb + c0, rc);
+    st4(density + sb + c0, rc);
+  }
+  float u[3][4];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (a < g.nc) {
+      ld4(tmp_u + ub + a * g.n + c0, u[a]);
+      if (bc.u_inv) {
+        float iv[4], bv[4];
+        ld4(bc.u_inv + ub + a * g.n + c0, iv);
+        ld4(bc.u_bc + ub + a * g.n + c0, bv);
+#pragma unroll
+        for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+      }
+    }
+  }
+  if (do_buoy && density) {
+    const QuadFlags q = quad_flags<IS3D>(flags + sb, g, c0, k, j, i0, false);
+    // density (after its BC) of the -x / -y / -z neighbours
+    float rl = 0.0f, ry[4], rz[4];
+    zero4(ry); zero4(rz);
+    if (i0 > 0) {
+      rl = __ldg(tmp_s + sb + c0 - 1);
+      if (bc.d_inv) { const float t = rl * __ldg(bc.d_inv + sb + c0 - 1); rl = t + __ldg(bc.d_bc + sb + c0 - 1); }
+    }
+    if (j > 0) dens_bc(sb + c0 - sy, ry);
+    if (IS3D && k > 0) dens_bc(sb + c0 - sz, rz);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      if (on_border(g, k, j, i0 + v) || !(q.c.c[v] & kFluid)) continue;
+      if (q.xm(v) & kFluid) u[0][v] += (0.5f * sx * (rc[v] + (v == 0 ? rl : rc[v - 1])));
+      if (q.ym.c[v] & kFluid) u[1][v] += (0.5f * sy_ * (rc[v] + ry[v]));
+      if (IS3D && (q.zm.c[v] & kFluid)) u[2][v] += (0.5f * sz_ * (rc[v] + rz[v]));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) if (a < g.nc) st4(U + ub + a * g.n + c0, u[a]);
+}
+
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_vort_bc_mask4(float* __restrict__ U, const unsigned char* __restrict__ flags,
+                                                       const float* __restrict__ force, int do_vort, BcPtrs bc,
+                                                       int mask_mode, double* __restrict__ sums, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  const bool live = thread_cell4(g, b, k, j, i0);
+  double s = 0.0, ss = 0.0;
+  if (live) {
+    const int c0 = cell(g, k, j, i0);
+    const int sy = g.nx, sz = g.nx * g.ny;
+    const long long ub = (long long)b * g.nc * g.n;
+    const QuadFlags q = quad_flags<IS3D>(flags + b * g.n, g, c0, k, j, i0, mask_mode != 0);
+    float u[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; a++) if (a < g.nc) ld4_rw(U + ub + a * g.n + c0, u[a]);
+    if (do_vort) {
+      const float* fb = force + (long long)b * 3 * g.n;
+      float fx[4], fy[4], fyl[4], fz[4], fzl[4];
+      ld4(fb + c0, fx);
+      const float fxl = i0 > 0 ? __ldg(fb + c0 - 1) : 0.0f;
+      ld4(fb + g.n + c0, fy);
+      zero4(fyl); zero4(fz); zero4(fzl);
+      if (j > 0) ld4(fb + g.n + c0 - sy, fyl);
+      if (IS3D) {
+        ld4(fb + 2 * g.n + c0, fz);
+        if (k > 0) ld4(fb + 2 * g.n + c0 - sz, fzl);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        if (on_border(g, k, j, i0 + v)) continue;
+        const int fc = q.c.c[v];
+        const bool cf = fc & kFluid, ce = fc & kEmpty;
+        if (!(cf || ce)) continue;
+        int f = q.xm(v);
+        if ((f & kFluid) || (cf && (f & kEmpty))) u[0][v] += (0.5f * ((v == 0 ? fxl : fx[v - 1]) + fx[v]));
+        f = q.ym.c[v];
+        if ((f & kFluid) || (cf && (f & kEmpty))) u[1][v] += (0.5f * (fyl[v] + fy[v]));
+        if (IS3D) {
+          f = q.zm.c[v];
+          if ((f & kFluid) || (cf && (f & kEmpty))) u[2][v] += (0.5f * (fzl[v] + fz[v]));
+        }
+      }
+    }
+    if (bc.u_inv) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (a < g.nc) {
+          float iv[4], bv[4];
+          ld4(bc.u_inv + ub + a * g.n + c0, iv);
+          ld4(bc.u_bc + ub + a * g.n + c0, bv);
+#pragma unroll
+          for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+        }
+      }
+    }
+    if (mask_mode) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        bool z[3];
+        wall_mask_from_flags(q.c.c[v], q.xm(v), q.xp(v), q.ym.c[v], q.yp.c[v], q.zm.c[v], q.zp.c[v], IS3D, z);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          if (a < g.nc) {
+            if (z[a]) u[a][v] = u[a][v] * 0.0f;
+            const float sq = u[a][v] * u[a][v];
+            s += (double)u[a][v];
+            ss += (double)sq;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) if (a < g.nc) st4(U + ub + a * g.n + c0, u[a]);
+  }
+  if (mask_mode) block_accumulate(s, ss, sums + 2 * (live ? b : 0));
+}
+
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_cnn_inputs_fused4(const float* __restrict__ p_div, const float* __restrict__ U1,
+                                                           const unsigned char* __restrict__ flags,
+                                                           const double* __restrict__ sums, float threshold,
+                                                           float* __restrict__ scale_out, float4* __restrict__ x0, int px,
+                                                           int py, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const int c0 = cell(g, k, j, i0);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const float sc = scale_from_sums(sums, b, (long long)g.nc * g.n, threshold);
+  if (c0 == 0) scale_out[b] = sc;
+  const float* ub = U1 + (long long)b * g.nc * g.n;
+  const Flags4 fc = flags4(flags + b * g.n + c0, true);
+  float ux[4], uy[4], uyp[4], uz[4], uzp[4], pd[4];
+  ld4(ub + c0, ux);
+  const float uxr = i0 + 4 < g.nx ? __ldg(ub + c0 + 4) : 0.0f;
+  ld4(ub + g.n + c0, uy);
+  zero4(uyp); zero4(uz); zero4(uzp);
+  if (j < g.ny - 1) ld4(ub + g.n + c0 + sy, uyp);
+  if (IS3D) {
+    ld4(ub + 2 * g.n + c0, uz);
+    if (k < g.nz - 1) ld4(ub + 2 * g.n + c0 + sz, uzp);
+  }
+  ld4(p_div + b * g.n + c0, pd);
+  const long long plane = (long long)(g.nz + 2) * py * px;
+  const long long o = (long long)b * 2 * plane + ((long long)(k + 1) * py + (j + 1)) * px + (i0 + 1);
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    const int f = fc.c[v];
+    float dv = 0.0f;
+    if (!on_border(g, k, j, i0 + v) && (f & kFluid)) {
+      dv = ux[v] - (v == 3 ? uxr : ux[v + 1]) + uy[v] - uyp[v];
+      if (IS3D) dv += (uz[v] - uzp[v]);
+    }
+    x0[o + v] = make_float4(pd[v] / sc, dv / sc, (f == kFluid) ? 0.0f : ((f == kObstacle) ? 1.0f : -1.0f), 0.0f);
+  }
+}
+
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_cnn_finish_fused4(const float* __restrict__ p_net, float* __restrict__ U,
+                                                           const unsigned char* __restrict__ flags,
+                                                           const float* __restrict__ scale, float* __restrict__ p_out,
+                                                           BcPtrs bc, float lo, float hi, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const int c0 = cell(g, k, j, i0);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const float sc = __ldg(scale + b);
+  const float* pb = p_net + b * g.n;
+  const long long ub = (long long)b * g.nc * g.n;
+  const QuadFlags q = quad_flags<IS3D>(flags + b * g.n, g, c0, k, j, i0, true);
+  float pc[4], py_[4], pz[4];
+  ld4(pb + c0, pc);
+  const float pl = i0 > 0 ? __ldg(pb + c0 - 1) : 0.0f;
+  zero4(py_); zero4(pz);
+  if (j > 0) ld4(pb + c0 - sy, py_);
+  if (IS3D && k > 0) ld4(pb + c0 - sz, pz);
+  float u[3][4];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (a < g.nc) {
+      ld4_rw(U + ub + a * g.n + c0, u[a]);
+#pragma unroll
+      for (int v = 0; v < 4; v++) u[a][v] = u[a][v] / sc;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    if (on_border(g, k, j, i0 + v)) continue;
+    const int fc = q.c.c[v];
+    const int fn[3] = {q.xm(v), q.ym.c[v], IS3D ? q.zm.c[v] : 0};
+    const float pn[3] = {v == 0 ? pl : pc[v - 1], py_[v], pz[v]};
+    if (fc & kFluid) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (a < g.nc) {
+          if (fn[a] & kFluid) u[a][v] -= (pc[v] - pn[a]);
+          if (fn[a] & kEmpty) u[a][v] -= pc[v];
+        }
+      }
+    } else if ((fc & kEmpty) && !(fc & kOutflow)) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (a < g.nc) {
+          if (fn[a] & kFluid) u[a][v] += pn[a];
+          else u[a][v] = 0.0f;
+        }
+      }
+    }
+  }
+  bool z[4][3];
+#pragma unroll
+  for (int v = 0; v < 4; v++)
+    wall_mask_from_flags(q.c.c[v], q.xm(v), q.xp(v), q.ym.c[v], q.yp.c[v], q.zm.c[v], q.zp.c[v], IS3D, z[v]);
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (a < g.nc) {
+      float iv[4] = {1.0f, 1.0f, 1.0f, 1.0f}, bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (bc.u_inv) {
+        ld4(bc.u_inv + ub + a * g.n + c0, iv);
+        ld4(bc.u_bc + ub + a * g.n + c0, bv);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        float w = u[a][v] * sc;
+        if (z[v][a]) w = w * 0.0f;
+        if (bc.u_inv) { const float t = w * iv[v]; w = t + bv[v]; }
+        w = (w < lo) ? lo : ((w > hi) ? hi : w);
+        u[a][v] = w;
+      }
+      st4(U + ub + a * g.n + c0, u[a]);
+    }
+  }
+  float po[4];
+#pragma unroll
+  for (int v = 0; v < 4; v++) po[v] = pc[v] * sc;
+  st4(p_out + b * g.n + c0, po);
+}
+
+// Rows the quad kernels cover: nx a multiple of 4 and a block shape that tiles 256 threads.
+static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
+  if (g.nx % 4 != 0 || g.zlo != 0 || g.zhi != g.nz) return false;
+  const int quads = g.nx / 4;
+  int bx;
+  if (quads >= 32) bx = 32;
+  else if ((quads & (quads - 1)) == 0) bx = quads;
+  else return false;
+  const int bz = g.nz > 1 ? 2 : 1;
+  const int by = 256 / (bx * bz);
+  block = dim3(bx, by, bz);
+  grid = dim3((quads + bx - 1) / bx, (g.ny + by - 1) / by, ((long long)g.nb * g.nz + bz - 1) / bz);
+  return true;
+}
+#define TFL_LAUNCH4F(kernel, g, grid_, block_, st, ...)                            \
+  do {                                                                              \
+    if ((g).is3d) kernel<true><<<grid_, block_, 0, st>>>(__VA_ARGS__);              \
+    else kernel<false><<<grid_, block_, 0, st>>>(__VA_ARGS__);                      \
+  } while (0)
+
 #define TFL_LAUNCH3F(kernel, g, st, ...)                                                \
   do {                                                                                  \
     dim3 grid_, block_;                                                                 \
@@ -207,23 +569,43 @@ void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned c
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, d_inv, d_bc};
+  dim3 qg, qb;
+  if (quad_dims(g, qg, qb)) {
+    TFL_LAUNCH4F(k_post_advect4, g, qg, qb, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
+    return;
+  }
   TFL_LAUNCH3F(k_post_advect, g, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
 }
 void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort,
                          const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
+  dim3 qg, qb;
+  if (quad_dims(g, qg, qb)) {
+    TFL_LAUNCH4F(k_vort_bc_mask4, g, qg, qb, st, U, flags, force, do_vort, bc, mask_mode, sums, g);
+    return;
+  }
   TFL_LAUNCH3F(k_vort_bc_mask, g, st, U, flags, force, do_vort, bc, mask_mode, sums, g);
 }
 void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
                              cudaStream_t st) {
+  dim3 qg, qb;
+  if (quad_dims(g, qg, qb)) {
+    TFL_LAUNCH4F(k_cnn_inputs_fused4, g, qg, qb, st, p_div, U1, flags, sums, threshold, scale_out, (float4*)x0, px, py, g);
+    return;
+  }
   TFL_LAUNCH3F(k_cnn_inputs_fused, g, st, p_div, U1, flags, sums, threshold, scale_out, (float4*)x0, px, py, g);
 }
 void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* flags, const float* scale, float* p_out,
                              const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
                              cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
+  dim3 qg, qb;
+  if (quad_dims(g, qg, qb)) {
+    TFL_LAUNCH4F(k_cnn_finish_fused4, g, qg, qb, st, p_net, U, flags, scale, p_out, bc, lo, hi, g);
+    return;
+  }
   TFL_LAUNCH3F(k_cnn_finish_fused, g, st, p_net, U, flags, scale, p_out, bc, lo, hi, g);
 }
 
