@@ -362,8 +362,13 @@ __device__ __forceinline__ bool thread_cell(const Geo& g, int& b, int& k, int& j
   j = blockIdx.y * blockDim.y + threadIdx.y;
   const int zz = blockIdx.z * blockDim.z + threadIdx.z;
   const int nzr = g.zhi - g.zlo;
-  b = zz / nzr;
-  k = g.zlo + (zz - b * nzr);
+  if (zz < nzr) {                       // first (usually only) batch element: no integer division
+    b = 0;
+    k = g.zlo + zz;
+  } else {
+    b = zz / nzr;
+    k = g.zlo + (zz - b * nzr);
+  }
   return i < g.nx && j < g.ny && b < g.nb;
 }
 

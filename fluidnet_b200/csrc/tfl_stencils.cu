@@ -353,6 +353,32 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
     const int k0 = g.is3d ? clamp_i((int)pz, 0, g.gnz - 1) : 0;
     float lo = INFINITY, hi = -INFINITY;
     int found = 0;
+    const int kl0 = k0 - g.zoff;
+    const bool interior = i0 >= 1 && i0 <= g.nx - 2 && j0 >= 1 && j0 <= g.ny - 2 &&
+                          (!g.is3d || (k0 >= 1 && k0 <= g.gnz - 2 && kl0 >= 1 && kl0 <= g.nz - 2));
+    if (interior) {
+      // Same cells in the same order as the general loop below, without its bounds tests: the
+      // 27 (9 in 2-D) neighbours sit at fixed offsets from the centre.
+      const int ctr = cell(g, g.is3d ? kl0 : 0, j0, i0);
+      const int sy = g.nx, sz = g.nx * g.ny;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++) {
+        if (!g.is3d && dz != 0) continue;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            const int o = ctr + dz * sz + dy * sy + dx;
+            const float t = __ldg(sb + o);
+            if (outside || (flag_at(fl, o) & kFluid)) {
+              if (t < lo) lo = t;
+              if (t > hi) hi = t;
+              found = 1;
+            }
+          }
+        }
+      }
+    } else {
     for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
       if (kk < 0 || kk >= g.gnz) continue;
       const int kl = local_z(g, kk);
@@ -368,6 +394,7 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
           }
         }
       }
+    }
     }
     v = (found < 1) ? fw : clamp_f(v, lo, hi);
   }
