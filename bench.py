@@ -423,7 +423,10 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "advectVel (k_advect_vel_pass1+pass2, maccormackOurs)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": 84.9e6 if n == 128 else None,   # ncu dram read+write, both passes (profiles/r01_ncu_summary.md)
-                     "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms},
+                     "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms,
+                     # ncu (profiles/r01_ncu_summary.md): this kernel pair is bound by instruction issue
+                     # (sm__issue_active 62-70 %, DRAM 4 %), so the HBM fraction is small by nature.
+                     "limiter": "instruction issue (ncu sm__issue_active 62-70 %, dram 4 %)"},
         "roofline_extra": extra,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
