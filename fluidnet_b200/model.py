@@ -49,6 +49,15 @@ class ProjectionModel:
         self.h = h
         self.last_scale = None
 
+    @classmethod
+    def from_reference_file(cls, model_path, mconf_path=None, device=None):
+        """A model saved by the reference (torch/lib/save_model.lua: Torch7 binary network + `_mconf.bin`),
+        read without Torch7 (fluidnet_b200/torch7.py).  Returns (model, mconf)."""
+        from . import torch7
+        ref = torch7.load_reference_model(model_path, mconf_path)
+        thr = ref["mconf"].get("normalizeInputThreshold", 1e-5)
+        return cls(ref["layers"], ref["is3D"], device=device, normalizeInputThreshold=thr), ref["mconf"]
+
     MODES = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
     def set_mode(self, mode):

@@ -144,7 +144,7 @@ def test_jacobi_marching_kernel(orc, gpu, shape):
         assert abs(ra - rb) <= 1e-5 * max(abs(rb), 1e-12) + 1e-12
 
 
-@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")))
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLD) if f.startswith("ref_") and f.endswith(".npz")))
 def test_gpu_matches_reference_golden(gpu, fname):
     """Against outputs of the reference's own CPU code (fixtures committed under
     tests/golden/, generated by tests/golden/make_golden.py)."""

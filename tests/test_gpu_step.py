@@ -159,6 +159,39 @@ def test_host_buffer_step_equals_device_step(method):
         lib.tfl_host_sim_destroy(ctx.h, hs)
 
 
+def test_trained_reference_model_2d(orc):
+    """The 2-D model the reference ships (data/models/myModel2D, read by fluidnet_b200/torch7.py; weights
+    committed as tests/golden/myModel2D_layers.npz): model:forward and three simulate steps with its
+    own mconf (maccormack advection, no buoyancy), against the oracle.  A trained projection must also do
+    its job: it leaves less divergence than it was given."""
+    import os
+    from fluidnet_b200 import simulate
+    from gpu_backend import make_gpu_model
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "myModel2D_layers.npz"))
+    mnp = {"is3D": bool(z["is3D"]), "layers": [(z["w%d" % i], z["b%d" % i]) for i in range(int(z["n_layers"]))]}
+    assert mnp["is3D"] is False
+    n = 64
+    batch = make_batch(n, False, plume=False, amp=1.0)
+    gm = make_gpu_model(mnp, threshold=float(z["normalizeInputThreshold"]))
+    p0 = np.zeros_like(batch["flags"])
+    wp, wU, wscale = oracle.model_forward(orc, mnp, p0, batch["UDiv"], batch["flags"])
+    gp, gU = gm.forward((torch.from_numpy(p0).cuda(), torch.from_numpy(batch["UDiv"]).cuda(),
+                         torch.from_numpy(batch["flags"]).cuda()), return_scale=True)
+    close(gp.cpu().numpy(), wp, 2e-5, "p")
+    close(gU.cpu().numpy(), wU, 2e-5, "U")
+    div_in = np.linalg.norm(orc.velocityDivergenceForward(batch["UDiv"], batch["flags"]))
+    div_out = np.linalg.norm(orc.velocityDivergenceForward(gU.cpu().numpy(), batch["flags"]))
+    assert div_out < 0.8 * div_in, (div_in, div_out)       # (this small model removes ~40 % per application)
+    mconf = oracle.default_mconf(dt=0.1, advectionMethod="maccormack", maccormackStrength=0.75, is3D=False,
+                                 simMethod="convnet")
+    gb = to_gpu(batch)
+    for step in range(3):
+        simulate.simulate(None, mconf, gb, gm)
+        oracle.simulate(orc, mconf, batch, mnp)
+        for k in ("density", "UDiv", "pDiv"):
+            close(gb[k].cpu().numpy(), batch[k], 2e-5 * (step + 1) * 5, "step %d %s" % (step, k))
+
+
 def test_full_size_properties():
     """BASELINE-size (128^3) checks that do not need the CPU oracle: the Jacobi-projected
     velocity is (nearly) divergence free, the obstacle faces stay exactly zero, advection of

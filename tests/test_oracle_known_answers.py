@@ -143,7 +143,7 @@ def test_no_displacement_is_not_traced(orc):
 def _golden_files():
     if not os.path.isdir(GOLD):
         return []
-    return sorted(f for f in os.listdir(GOLD) if f.endswith(".npz"))
+    return sorted(f for f in os.listdir(GOLD) if f.startswith("ref_") and f.endswith(".npz"))
 
 
 @pytest.mark.parametrize("fname", _golden_files())
