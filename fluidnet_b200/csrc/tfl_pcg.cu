@@ -14,8 +14,9 @@
 //   * no matrix: a 16-bit code per cell (in-system, 6 links, diagonal count, preconditioner on);
 //   * IC(0) / ILU(0) (one operator for a symmetric matrix) in the system's lexicographic order, like
 //     csric0 + two csrsv.  The triangular solves are wavefront-sequential; they run as a pipeline of
-//     persistent CTAs over a SKEWED layout: cell (i, j) of plane k is stored at row s = i + j, so a
-//     2-D wavefront is one contiguous row, a thread owns grid row j and carries its x-neighbour in a
+//     persistent CTAs over a SKEWED layout: cell (i, j) of plane k is stored at row (i + j) mod
+//     max(nx, ny), column j -- a bijection onto a compact array in which a 2-D wavefront i + j = s is
+//     (part of) one contiguous row, a thread owns grid row j and carries its x-neighbour in a
 //     register, the y-neighbour comes from the adjacent thread through shared memory and the
 //     z-neighbour from the thread group one plane below, which runs one step ahead in the same CTA
 //     (shared memory) or in the previous CTA (global memory + a progress word).  Every vector of the
@@ -40,15 +41,17 @@ constexpr long long kSpinLimit = 1ll << 22;
 
 struct PcgGeo {
   int nx, ny, nz, nb, is3d;
-  int S, NYP, P;           // skew rows per plane, padded row length, planes (nb * nz)
+  int S, NYP, P;           // wavefronts per plane (nx + ny - 1), padded row length, planes (nb * nz)
+  int R;                   // rows stored per plane: wavefront s lives in row s mod R, R = max(nx, ny)
   long long n;             // cells per batch element
-  long long plane;         // S * NYP
+  long long plane;         // R * NYP
   long long slots;         // P * plane
   int GP, chunks;          // planes per CTA, plane chunks
 };
 
 __device__ __forceinline__ long long skew_index(const PcgGeo& g, int pl, int j, int i) {
-  return ((long long)pl * g.S + (i + j)) * g.NYP + j;
+  const int s = i + j;
+  return ((long long)pl * g.R + (s >= g.R ? s - g.R : s)) * g.NYP + j;
 }
 
 // ---- connected components (union-find, lock-free) ----------------------------------------
@@ -210,8 +213,14 @@ __global__ void k_direction_spmv(const unsigned short* __restrict__ cf, const in
                                  float* __restrict__ p_new, float* __restrict__ w, CompScalars sc, PcgGeo g,
                                  int no_precond) {
   CompAcc a;
-  const long long row = g.NYP, pl = g.plane;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < g.slots; q += (long long)gridDim.x * blockDim.x) {
+  const long long pl = g.plane;
+  const int j = threadIdx.x;                      // blockDim.x == NYP: one stored row per block iteration
+  for (long long row = blockIdx.x; row < (long long)g.P * g.R; row += gridDim.x) {
+    const int r = (int)(row % g.R);
+    // rows of the -x / +x neighbours (the wavefront index wraps around the R stored rows)
+    const long long dm = r > 0 ? -(long long)g.NYP : (long long)(g.R - 1) * g.NYP;
+    const long long dp = r < g.R - 1 ? (long long)g.NYP : -(long long)(g.R - 1) * g.NYP;
+    const long long q = row * g.NYP + j;
     const unsigned c = cf[q];
     if (!(c & kInSys)) continue;
     const int id = comp[q];
@@ -223,10 +232,10 @@ __global__ void k_direction_spmv(const unsigned short* __restrict__ cf, const in
     }
     const float ps = z[q] + beta * p_old[q];
     float acc = (float)((c >> kDiagShift) & 7u) * ps;
-    if (c & kXM) acc -= z[q - row] + beta * p_old[q - row];
-    if (c & kXP) acc -= z[q + row] + beta * p_old[q + row];
-    if (c & kYM) acc -= z[q - row - 1] + beta * p_old[q - row - 1];
-    if (c & kYP) acc -= z[q + row + 1] + beta * p_old[q + row + 1];
+    if (c & kXM) acc -= z[q + dm] + beta * p_old[q + dm];
+    if (c & kXP) acc -= z[q + dp] + beta * p_old[q + dp];
+    if (c & kYM) acc -= z[q + dm - 1] + beta * p_old[q + dm - 1];
+    if (c & kYP) acc -= z[q + dp + 1] + beta * p_old[q + dp + 1];
     if (c & kZM) acc -= z[q - pl] + beta * p_old[q - pl];
     if (c & kZP) acc -= z[q + pl] + beta * p_old[q + pl];
     p_new[q] = ps;
@@ -412,6 +421,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
   // pre = 0, which makes their results 0.  In 2-D the planes of a CTA are different batch elements and
   // the z term is switched off.
   const int ticks4 = (ticks + 3) & ~3;          // the tick loops are unrolled by 4; surplus ticks do nothing
+  auto row_of = [&](int s) { return s >= g.R ? s - g.R : s; };   // stored row of wavefront s
   const float use_z = g.is3d ? 1.0f : 0.0f;
 
   // ---------------- forward: R^T y = r (or the factor) ----------------
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
       const int pl = chunk * g.GP + gq;
       const bool plane_ok = pl < g.P && j < g.ny;
       const bool from_global = wait_below && gq == 0;
-      const long long plane0 = (long long)pl * g.S * g.NYP + j;
+      const long long plane0 = (long long)pl * g.plane + j;
       const unsigned short* p_cf = a.cf + plane0;
       const float* p_r = a.r + plane0;
       float* p_pre = a.pre + plane0;
@@ -445,8 +455,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
         Slot f;
         f.c = 0; f.r = 0.0f; f.pre = 0.0f; f.z = 0.0f; f.nb = 0.0f; f.nb2 = 0.0f;
         const int s = tick - gq;
-        if (plane_ok && (unsigned)s < (unsigned)g.S) {
-          const int off = s * g.NYP;
+        if (plane_ok && (unsigned)(s - j) < (unsigned)g.nx) {        // cell (s - j, j) exists
+          const int off = (s >= g.R ? s - g.R : s) * g.NYP;
           f.c = p_cf[off];
           if (!FACTOR) { f.r = p_r[off]; f.pre = p_pre[off]; }
           if (from_global) {                   // no arithmetic here: a use would wait for the loads
@@ -477,11 +487,11 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
             float e = dg - carry * carry - ym * ym - zm * zm;
             if (!(e > 1e-6f * dg)) e = dg;                     // vanishing pivot guard
             const float pv = on != 0.0f ? 1.0f / sqrtf(e) : 1.0f;
-            if (f.c & kInSys) __stcg(p_pre + (tick - gq) * g.NYP, pv);
+            if (f.c & kInSys) __stcg(p_pre + row_of(tick - gq) * g.NYP, pv);
             out = on * pv;
           } else {
             const float y = (f.r + carry + ym + zm) * f.pre;
-            if (f.c & kInSys) __stcg(p_z + (tick - gq) * g.NYP, y);
+            if (f.c & kInSys) __stcg(p_z + row_of(tick - gq) * g.NYP, y);
             out = on * f.pre * y;
           }
           carry = out;
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
       const bool plane_ok = pl < g.P && j < g.ny;
       const bool from_global = wait_above && gq == g.GP - 1;
       const int lag = g.GP - 1 - gq;            // the top group leads
-      const long long plane0 = (long long)pl * g.S * g.NYP + j;
+      const long long plane0 = (long long)pl * g.plane + j;
       const unsigned short* p_cf = a.cf + plane0;
       const float* p_r = a.r + plane0;
       const float* p_pre = a.pre + plane0;
@@ -530,8 +540,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
         Slot f;
         f.c = 0; f.r = 0.0f; f.pre = 0.0f; f.z = 0.0f; f.nb = 0.0f; f.nb2 = 0.0f;
         const int st = tick - lag;
-        if (plane_ok && (unsigned)st < (unsigned)g.S) {
-          const int off = (g.S - 1 - st) * g.NYP;
+        const int s = g.S - 1 - st;
+        if (plane_ok && (unsigned)(s - j) < (unsigned)g.nx) {
+          const int off = row_of(s) * g.NYP;
           f.c = p_cf[off];
           f.r = p_r[off];
           f.pre = p_pre[off];
@@ -557,7 +568,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep(SweepArgs a, PcgGeo g) {
           const float on = (f.c & kPreOn) ? 1.0f : 0.0f;
           const float out = (f.z + f.pre * on * (carry + yp + zp)) * f.pre;
           if (f.c & kInSys) {
-            const int off = (g.S - 1 - (tick - lag)) * g.NYP;
+            const int off = row_of(g.S - 1 - (tick - lag)) * g.NYP;
             __stcg(p_z + off, out);
             racc.add(a.rz, p_comp[off], (double)f.r * (double)out);
           }
@@ -601,7 +612,7 @@ inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 size_t pcg_workspace_bytes(int nb, int nz, int ny, int nx) {
   const long long cells = (long long)nb * nz * ny * nx;
   const long long NYP = (ny + 31) / 32 * 32;
-  const long long slots = (long long)nb * nz * (nx + ny - 1) * NYP;
+  const long long slots = (long long)nb * nz * (nx > ny ? nx : ny) * NYP;
   return (size_t)(cells * 12 + slots * (2 + 4 + 7 * 4) + 16 * 256 + 1024);
 }
 
@@ -627,7 +638,8 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
   g.NYP = (ny + 31) / 32 * 32;
   g.P = nb * nz;
   g.n = (long long)nz * ny * nx;
-  g.plane = (long long)g.S * g.NYP;
+  g.R = nx > ny ? nx : ny;
+  g.plane = (long long)g.R * g.NYP;
   g.slots = (long long)g.P * g.plane;
   if (g.NYP > 960) return 4;
   g.GP = (1024 - 64) / g.NYP;      // two service warps per CTA (gate, talk)
@@ -747,7 +759,7 @@ int pcg_solve(PcgScratch& sc, void* workspace, float* p, const float* flags, con
     for (int rep = 0; rep < 4; rep++) {
       PCG_CUDA(cudaMemsetAsync(header, 0, 4, st));
       if (!no_precond) PCG_CUDA(launch_sweep(false));
-      k_direction_spmv<<<ew_blocks, 256, 0, st>>>(cf, comp, no_precond ? r : z, p_old, p_new, w, cs, g, no_precond);
+      k_direction_spmv<<<ew_blocks, g.NYP, 0, st>>>(cf, comp, no_precond ? r : z, p_old, p_new, w, cs, g, no_precond);
       k_update<<<ew_blocks, 256, 0, st>>>(cf, comp, p_new, w, x, r, cs, g.slots, no_precond);
       k_scalars<<<(ncomp + 255) / 256, 256, 0, st>>>(cs, ncomp, tol2, max_iter, 0, no_precond);
       *launches += 3;
@@ -788,7 +800,7 @@ int normalize_pressure_mean(void* workspace, float* p, const float* flags, int n
   PcgGeo g;
   g.nx = nx; g.ny = ny; g.nz = nz; g.nb = nb; g.is3d = is3d ? 1 : 0;
   g.n = (long long)nz * ny * nx;
-  g.S = 0; g.NYP = 0; g.P = nb * nz; g.plane = 0; g.slots = 0; g.GP = 1; g.chunks = 0;
+  g.S = 0; g.NYP = 0; g.R = 0; g.P = nb * nz; g.plane = 0; g.slots = 0; g.GP = 1; g.chunks = 0;
   const long long cells = g.n * nb;
   char* base = (char*)workspace;
   size_t off = 0;
