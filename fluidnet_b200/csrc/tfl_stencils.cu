@@ -366,15 +366,16 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
         if (!g.is3d && dz != 0) continue;
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++) {
+          // one pointer pair per row: the three cells of a row are immediate offsets -1, 0, +1
+          const float* srow = sb + (ctr + dz * sz + dy * sy);
+          const FT* frow = fl + (ctr + dz * sz + dy * sy);
 #pragma unroll
           for (int dx = -1; dx <= 1; dx++) {
-            const int o = ctr + dz * sz + dy * sy + dx;
-            const float t = __ldg(sb + o);
-            if (outside || (flag_at(fl, o) & kFluid)) {
-              if (t < lo) lo = t;
-              if (t > hi) hi = t;
-              found = 1;
-            }
+            const float t = __ldg(srow + dx);
+            const bool use = outside || (flag_at(frow, dx) & kFluid);
+            lo = (use && t < lo) ? t : lo;
+            hi = (use && t > hi) ? t : hi;
+            found |= use ? 1 : 0;
           }
         }
       }
@@ -557,10 +558,14 @@ __device__ __forceinline__ float clamp_component_mac(const float* __restrict__ o
     const int kl0 = local_z(g, k0), kl1 = g.is3d ? local_z(g, k1) : kl0;
 // The eight corners sit at fixed offsets from the first one (same visiting order as the reference).
     const float* a0 = orig_c + cell(g, kl0, j0, i0);
-    const int dzo = (kl1 - kl0) * g.ny * g.nx;
-#define TFL_MM(off) { const float t = __ldg(a0 + (off)); if (t < lo) lo = t; if (t > hi) hi = t; }
-    TFL_MM(0) TFL_MM(1) TFL_MM(g.nx) TFL_MM(g.nx + 1)
-    if (g.is3d) { TFL_MM(dzo) TFL_MM(dzo + 1) TFL_MM(dzo + g.nx) TFL_MM(dzo + g.nx + 1) }
+    const float* a1 = a0 + g.nx;
+#define TFL_MM(ptr, off) { const float t = __ldg((ptr) + (off)); if (t < lo) lo = t; if (t > hi) hi = t; }
+    TFL_MM(a0, 0) TFL_MM(a0, 1) TFL_MM(a1, 0) TFL_MM(a1, 1)
+    if (g.is3d) {
+      const float* b0 = a0 + (kl1 - kl0) * g.ny * g.nx;
+      const float* b1 = b0 + g.nx;
+      TFL_MM(b0, 0) TFL_MM(b0, 1) TFL_MM(b1, 0) TFL_MM(b1, 1)
+    }
 #undef TFL_MM
   }
   return clamp_f(val, lo, hi);
