@@ -537,6 +537,135 @@ __global__ void __launch_bounds__(256) k_cnn_finish_fused4(const float* __restri
   st4(p_out + b * g.n + c0, po);
 }
 
+// Six values of a row around a quad: x = i0 - 1 .. i0 + 4 (0 where the row or the cell is outside the grid).
+__device__ __forceinline__ void row6(const float* __restrict__ p, bool row_ok, bool has_left, bool has_right,
+                                     float (&o)[6]) {
+  if (!row_ok) { o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f; return; }
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = has_left ? __ldg(p - 1) : 0.0f;
+  o[1] = v.x; o[2] = v.y; o[3] = v.z; o[4] = v.w;
+  o[5] = has_right ? __ldg(p + 4) : 0.0f;
+}
+
+// k_vort_curl for a quad: curl of the cell-centred velocity (GetCentered + GetCurl,
+// third_party/tfluids.cc:1342-1409) with the centred velocity of border cells taken as zero.
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_vort_curl4(const float* __restrict__ U, float* __restrict__ curl,
+                                                    float* __restrict__ cnorm, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const int c0 = cell(g, k, j, i0);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const float* ux = U + (long long)b * g.nc * g.n + c0;
+  const float* uy = ux + g.n;
+  const float* uz = ux + 2 * g.n;                       // only dereferenced in 3-D
+  float wx[4], wy[4], wz[4], nr[4];
+  zero4(wx); zero4(wy); zero4(wz); zero4(nr);
+  const bool row_interior = j >= 1 && j <= g.ny - 2 && (!IS3D || (k >= 1 && k <= g.nz - 2));
+  if (row_interior) {
+    const bool hl = i0 > 0, hr = i0 + 4 < g.nx;
+    // centred y (and z) velocity along this row, x = i0 - 1 .. i0 + 4
+    float a[6], bb[6], cy[6], cz[6];
+    row6(uy, true, hl, hr, a);
+    row6(uy + sy, true, hl, hr, bb);
+#pragma unroll
+    for (int t = 0; t < 6; t++) cy[t] = 0.5f * (a[t] + bb[t]);
+    if (IS3D) {
+      row6(uz, true, hl, hr, a);
+      row6(uz + sz, true, hl, hr, bb);
+#pragma unroll
+      for (int t = 0; t < 6; t++) cz[t] = 0.5f * (a[t] + bb[t]);
+    }
+    // centred x velocity on the rows j +- 1 (and k +- 1), x = i0 .. i0 + 3; zero if that row is a border row
+    const bool yp_ok = j + 1 <= g.ny - 2, ym_ok = j - 1 >= 1;
+    const bool zp_ok = IS3D && k + 1 <= g.nz - 2, zm_ok = IS3D && k - 1 >= 1;
+    float cx_yp[4], cx_ym[4], cx_zp[4], cx_zm[4], cz_yp[4], cz_ym[4], cy_zp[4], cy_zm[4];
+    auto centred_x = [&](const float* row, bool ok, float (&o)[4]) {
+      float r6[6];
+      row6(row, ok, false, hr, r6);                     // r6[1..5] = x = i0 .. i0 + 4
+#pragma unroll
+      for (int v = 0; v < 4; v++) o[v] = ok ? 0.5f * (r6[1 + v] + r6[2 + v]) : 0.0f;
+    };
+    auto centred_2rows = [&](const float* r0, const float* r1, bool ok, float (&o)[4]) {
+      float p[4], q[4];
+      if (ok) { ld4(r0, p); ld4(r1, q); } else { zero4(p); zero4(q); }
+#pragma unroll
+      for (int v = 0; v < 4; v++) o[v] = ok ? 0.5f * (p[v] + q[v]) : 0.0f;
+    };
+    centred_x(ux + sy, yp_ok, cx_yp);
+    centred_x(ux - sy, ym_ok, cx_ym);
+    if (IS3D) {
+      centred_x(ux + sz, zp_ok, cx_zp);
+      centred_x(ux - sz, zm_ok, cx_zm);
+      centred_2rows(uz + sy, uz + sy + sz, yp_ok, cz_yp);
+      centred_2rows(uz - sy, uz - sy + sz, ym_ok, cz_ym);
+      centred_2rows(uy + sz, uy + sz + sy, zp_ok, cy_zp);
+      centred_2rows(uy - sz, uy - sz + sy, zm_ok, cy_zm);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int i = i0 + v;
+      if (i < 1 || i > g.nx - 2) continue;
+      const bool xp_ok = i + 1 <= g.nx - 2, xm_ok = i - 1 >= 1;
+      const float xp_y = xp_ok ? cy[v + 2] : 0.0f, xm_y = xm_ok ? cy[v] : 0.0f;
+      V3 w = {0.0f, 0.0f, 0.0f};
+      w.z = 0.5f * ((xp_y - xm_y) - (cx_yp[v] - cx_ym[v]));
+      if (IS3D) {
+        const float xp_z = xp_ok ? cz[v + 2] : 0.0f, xm_z = xm_ok ? cz[v] : 0.0f;
+        w.x = 0.5f * ((cz_yp[v] - cz_ym[v]) - (cy_zp[v] - cy_zm[v]));
+        w.y = 0.5f * ((cx_zp[v] - cx_zm[v]) - (xp_z - xm_z));
+      }
+      wx[v] = w.x; wy[v] = w.y; wz[v] = w.z;
+      nr[v] = norm3(w);
+    }
+  }
+  float* cb = curl + (long long)b * 3 * g.n + c0;
+  st4(cb, wx); st4(cb + g.n, wy); st4(cb + 2 * g.n, wz);
+  st4(cnorm + b * g.n + c0, nr);
+}
+
+// k_vort_force for a quad (conf_force of tfl_device.cuh, same arithmetic).
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_vort_force4(const float* __restrict__ curl, const float* __restrict__ cnorm,
+                                                     float* __restrict__ force, float strength, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const int c0 = cell(g, k, j, i0);
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const float* cn = cnorm + b * g.n + c0;
+  const float* cb = curl + (long long)b * 3 * g.n + c0;
+  float fx[4], fy[4], fz[4];
+  zero4(fx); zero4(fy); zero4(fz);
+  const bool row_interior = j >= 1 && j <= g.ny - 2 && (!IS3D || (k >= 1 && k <= g.nz - 2));
+  if (row_interior) {
+    float n6[6], nyp[4], nym[4], nzp[4], nzm[4], w0[4], w1[4], w2[4];
+    row6(cn, true, i0 > 0, i0 + 4 < g.nx, n6);
+    ld4(cn + sy, nyp); ld4(cn - sy, nym);
+    zero4(nzp); zero4(nzm);
+    if (IS3D) { ld4(cn + sz, nzp); ld4(cn - sz, nzm); }
+    ld4(cb, w0); ld4(cb + g.n, w1); ld4(cb + 2 * g.n, w2);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int i = i0 + v;
+      if (i < 1 || i > g.nx - 2) continue;
+      V3 gr = {0.0f, 0.0f, 0.0f};
+      gr.x = 0.5f * (n6[v + 2] - n6[v]);
+      gr.y = 0.5f * (nyp[v] - nym[v]);
+      if (IS3D) gr.z = 0.5f * (nzp[v] - nzm[v]);
+      const float gn = norm3(gr);
+      if (gn > 1e-6f) { gr.x /= gn; gr.y /= gn; gr.z /= gn; } else { gr.x = gr.y = gr.z = 0.0f; }
+      const V3 w = {w0[v], w1[v], w2[v]};
+      fx[v] = ((gr.y * w.z) - (gr.z * w.y)) * strength;
+      fy[v] = ((gr.z * w.x) - (gr.x * w.z)) * strength;
+      fz[v] = ((gr.x * w.y) - (gr.y * w.x)) * strength;
+    }
+  }
+  float* fb = force + (long long)b * 3 * g.n + c0;
+  st4(fb, fx); st4(fb + g.n, fy); st4(fb + 2 * g.n, fz);
+}
+
 // Rows the quad kernels cover: nx a multiple of 4 and a block shape that tiles 256 threads.
 static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
   if (g.nx % 4 != 0 || g.zlo != 0 || g.zhi != g.nz) return false;
@@ -564,6 +693,16 @@ static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
     if ((g).is3d) kernel<true, unsigned char><<<grid_, block_, 0, st>>>(__VA_ARGS__);   \
     else kernel<false, unsigned char><<<grid_, block_, 0, st>>>(__VA_ARGS__);           \
   } while (0)
+
+// Quad versions of curl + force over the whole grid; false if the shape does not fit (caller falls back).
+bool launch_vort_curl_quad(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
+                           cudaStream_t st) {
+  dim3 qg, qb;
+  if (!quad_dims(g, qg, qb)) return false;
+  TFL_LAUNCH4F(k_vort_curl4, g, qg, qb, st, U, curl, cnorm, g);
+  TFL_LAUNCH4F(k_vort_force4, g, qg, qb, st, curl, cnorm, force, strength, g);
+  return true;
+}
 
 void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,

@@ -60,6 +60,8 @@ void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned c
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
 void launch_vort_curl(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
                       cudaStream_t st);
+bool launch_vort_curl_quad(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
+                           cudaStream_t st);
 void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st);
 void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,

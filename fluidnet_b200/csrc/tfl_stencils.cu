@@ -900,6 +900,9 @@ void launch_add_gravity(float* U, const FT* flags, const float f[3], const Geo& 
 // [zlo, zhi) reads).  force always has 3 channels.
 void launch_vort_curl(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
                       cudaStream_t st) {
+  if (g.zlo == 0 && g.zhi == g.nz && g.zoff == 0 && g.gnz == g.nz &&
+      launch_vort_curl_quad(U, curl, cnorm, force, strength, g, st))
+    return;                                              // whole grid on one GPU: 4 voxels per thread
   Geo g1 = g;
   g1.zlo = g.zlo - 2 < 0 ? 0 : g.zlo - 2;
   g1.zhi = g.zhi + 1 > g.nz ? g.nz : g.zhi + 1;

@@ -93,6 +93,23 @@ def test_pointwise_operators(orc, gpu, case):
     assert bits_equal(a, b), "clamp " + describe_diff(a, b)
 
 
+@pytest.mark.parametrize("shape,is3d", [((32, 12, 10), True), ((128, 6, 5), True), ((16, 20, 1), False),
+                                        ((160, 8, 1), False)],
+                         ids=["32x12x10", "128x6x5", "16x20-2d", "160x8-2d"])
+def test_vorticity_quad_kernels(orc, gpu, shape, is3d):
+    """Row lengths that select the 4-voxels-per-thread curl / force kernels (nx % 4 == 0 and a block shape
+    that tiles): bit-exact against the oracle, geometry and exotic flags included."""
+    from fluidnet_b200 import synth
+    nx, ny, nz = shape
+    fl = synth.make_flags(nx, ny, nz, is3d, nb=2, geometry=True, exotic=True)
+    U = synth.make_velocity(fl, is3d, amp=3.0)
+    orc.setWallBcsForward(U, fl)
+    a, b = U.copy(), U.copy()
+    gpu.vorticityConfinement(a, fl, 0.3)
+    orc.vorticityConfinement(b, fl, 0.3)
+    assert bits_equal(a, b), "vorticityConfinement (quad) " + describe_diff(a, b)
+
+
 def test_empty_domain_and_occupancy(orc, gpu):
     for is3d, shape in ((True, (2, 1, 7, 9, 11)), (False, (2, 1, 1, 9, 11))):
         for bnd in (1, 2):
