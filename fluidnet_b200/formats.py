@@ -88,3 +88,48 @@ def load_vbox(path):
         a = np.fromfile(f, dtype=np.float32)
     n = a.size // (rx * ry * rz)
     return a[:n * rx * ry * rz].reshape(n, rx, ry, rz).transpose(0, 3, 2, 1)
+
+
+def load_binvox(path):
+    """tfluids.loadVoxelData (torch/lib/obstacles_import_binvox.lua:39-120): a `.binvox` occupancy volume
+    (ASCII header `#binvox 1` / `dim a b c` / `translate ...` / `scale s` / `data`, then run-length pairs
+    (value byte, count byte)) -> {'dims', 'translation', 'scale', 'data'} with data float32 of shape
+    [dims0][dims2][dims1] (the reference's `view(d0, d1, d2):permute(1, 3, 2)`).
+
+    Restated with the reference parser's behaviour, not the format's ideal: a run writes its value to
+    `count + 1` cells (the extra cell is overwritten by the next run) and the LAST run of the file is
+    dropped, because the loop stops writing once the read position reaches the end of the file
+    (`if (file:position() < endPosition)`, :93) -- so the cell after the second-to-last run keeps that
+    run's value and the rest of the last run stays 0.  Kept for byte-exact reproduction of what the
+    reference feeds its simulations."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    pos = 0
+    lines = []
+    for _ in range(5):
+        end = raw.index(b"\n", pos)
+        lines.append(raw[pos:end].decode("ascii").strip())
+        pos = end + 1
+    if not lines[0].startswith("#binvox"):
+        raise ValueError("%s: not a binvox file" % path)
+    dims = [int(v) for v in lines[1].split()[1:4]]
+    translation = [float(v) for v in lines[2].split()[1:4]]
+    scale = float(lines[3].split()[1])
+    count_total = dims[0] * dims[1] * dims[2]
+    data = np.zeros(count_total + 1, np.uint8)
+    body = raw[pos:]
+    index = 0                     # 0-based version of the reference's 1-based `index`
+    end_index = 0
+    read = 0
+    while end_index + 1 < count_total and read + 2 <= len(body):
+        value, count = body[read], body[read + 1]
+        read += 2
+        if read < len(body):      # the reference's position test: the final pair is read but not applied
+            end_index = index + count
+            if end_index + 1 > count_total:
+                raise ValueError("%s: run-length data overruns the volume" % path)
+            data[index:end_index + 1] = value
+            index = end_index
+    vol = data[:count_total].reshape(dims[0], dims[1], dims[2]).transpose(0, 2, 1)
+    return {"dims": dims, "translation": translation, "scale": scale,
+            "data": np.ascontiguousarray(vol, np.float32)}

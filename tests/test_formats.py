@@ -47,3 +47,24 @@ def test_vbox_layout(tmp_path):
     body = np.frombuffer(raw[16:], np.float32).reshape(2, res, res, res)     # [frame][x][y][z]
     assert body[0, 1, 2, 3] == frames[0][3, 2, 1]
     assert np.array_equal(formats.load_vbox(str(path)), np.stack(frames))
+
+
+def test_binvox_reader(tmp_path):
+    """Run-length volume with the reference parser's quirks (obstacles_import_binvox.lua:62-120)."""
+    dims = (3, 4, 2)
+    vol = np.zeros(24, np.uint8)
+    vol[5:9] = 1
+    vol[15:20] = 1
+    vol[20] = 1          # quirk: the 4th run writes count + 1 cells and the (dropped) last run never overwrites it
+    runs = [(0, 5), (1, 4), (0, 6), (1, 5), (0, 4)]                  # covers all 24 voxels; the last run is all zeros
+    raw = b"#binvox 1\ndim 3 4 2\ntranslate 0.5 -1 2\nscale 1.25\ndata\n" + bytes(b for r in runs for b in r)
+    path = tmp_path / "o.binvox"
+    path.write_bytes(raw)
+    out = formats.load_binvox(str(path))
+    assert out["dims"] == [3, 4, 2] and out["translation"] == [0.5, -1.0, 2.0] and out["scale"] == 1.25
+    assert out["data"].shape == (3, 2, 4) and out["data"].dtype == np.float32
+    assert np.array_equal(out["data"], vol.reshape(dims).transpose(0, 2, 1))
+    # the reference drops the final run: make it non-empty and it is not applied
+    runs2 = [(0, 5), (1, 4), (0, 6), (1, 5), (1, 4)]
+    path.write_bytes(raw[:raw.index(b"data\n") + 5] + bytes(b for r in runs2 for b in r))
+    assert np.array_equal(formats.load_binvox(str(path))["data"], out["data"])
