@@ -39,7 +39,8 @@ SYMBOLS = [
     "tfl_set_wall_bcs_forward", "tfl_velocity_divergence_forward", "tfl_velocity_update_forward",
     "tfl_add_buoyancy", "tfl_add_gravity", "tfl_vorticity_confinement",
     "tfl_solve_linear_system_jacobi", "tfl_solve_linear_system_pcg", "tfl_precond_from_string", "tfl_normalize_pressure_mean",
-    "tfl_volumetric_up_sampling_nearest_forward", "tfl_rectangular_blur", "tfl_signed_distance_field", "tfl_empty_domain", "tfl_flags_to_occupancy", "tfl_apply_bc",
+    "tfl_volumetric_up_sampling_nearest_forward", "tfl_rectangular_blur", "tfl_signed_distance_field", "tfl_velocity_divergence_backward",
+    "tfl_velocity_update_backward", "tfl_volumetric_up_sampling_nearest_backward", "tfl_empty_domain", "tfl_flags_to_occupancy", "tfl_apply_bc",
     "tfl_clamp", "tfl_cnn_create", "tfl_cnn_destroy", "tfl_cnn_set_mode", "tfl_cnn_get_mode", "tfl_cnn_project", "tfl_simulate_step",
     "tfl_host_sim_create", "tfl_host_sim_destroy", "tfl_host_sim_step",
 ]
@@ -89,6 +90,9 @@ def load():
     lib.tfl_volumetric_up_sampling_nearest_forward.argtypes = [C.c_void_p, C.c_int, G, G]
     lib.tfl_rectangular_blur.argtypes = [C.c_void_p, G, C.c_int, C.c_int, G]
     lib.tfl_signed_distance_field.argtypes = [C.c_void_p, G, C.c_int, C.c_int, G]
+    lib.tfl_velocity_divergence_backward.argtypes = [C.c_void_p, G, G, G, G]
+    lib.tfl_velocity_update_backward.argtypes = [C.c_void_p, G, G, G, G, G]
+    lib.tfl_volumetric_up_sampling_nearest_backward.argtypes = [C.c_void_p, C.c_int, G, G, G]
     lib.tfl_empty_domain.argtypes = [C.c_void_p, G, C.c_int, C.c_int]
     lib.tfl_flags_to_occupancy.argtypes = [C.c_void_p, G, G, C.POINTER(C.c_int64)]
     lib.tfl_apply_bc.argtypes = [C.c_void_p, G, G, G]

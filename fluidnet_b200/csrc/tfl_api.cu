@@ -618,6 +618,45 @@ int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_ra
   return check_launch(ctx, "signedDistanceField");
 }
 
+int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* go,
+                                     const tfl_grid* gU) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, go, "gradOutput")) return 1;
+  if (!gU || !gU->data || gU->nc != U->nc || !same_spatial(gU, U) || !same_spatial(go, flags)) return fail(ctx, "Size mismatch");
+  if (ctx->slab) return fail(ctx, "backward operators: single GPU only");
+  launch_velocity_divergence_backward(flags->data, go->data, gU->data, flags->nb, flags->nz, flags->ny, flags->nx,
+                                      U->nc == 3, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "velocityDivergenceBackward");
+}
+
+int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p,
+                                 const tfl_grid* go, const tfl_grid* gp) {
+  if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p") ||
+      check_scalar(ctx, gp, "gradP"))
+    return 1;
+  if (!go || !go->data || go->nc != U->nc || !same_spatial(go, U) || !same_spatial(gp, p) || !same_spatial(p, flags))
+    return fail(ctx, "Size mismatch");
+  if (ctx->slab) return fail(ctx, "backward operators: single GPU only");
+  launch_velocity_update_backward(flags->data, go->data, gp->data, flags->nb, flags->nz, flags->ny, flags->nx,
+                                  U->nc == 3, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "velocityUpdateBackward");
+}
+
+int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* go,
+                                                const tfl_grid* gi) {
+  if (!in || !go || !gi || !in->data || !go->data || !gi->data)
+    return fail(ctx, "ERROR: input, gradOutput and gradInput must be dim 5");
+  if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
+  if (go->nb != in->nb || go->nc != in->nc || go->nz != in->nz * ratio || go->ny != in->ny * ratio ||
+      go->nx != in->nx * ratio)
+    return fail(ctx, "ERROR: input : gradOutput size mismatch.");          // generic/tfluids.cc:584-590
+  if (!same_spatial(gi, in) || gi->nc != in->nc) return fail(ctx, "ERROR: input : gradInput size mismatch.");
+  launch_upsample_nearest_backward(go->data, gi->data, in->nb * in->nc, in->nz, in->ny, in->nx, ratio, ctx->stream);
+  ctx->launches += 1;
+  return check_launch(ctx, "volumetricUpSamplingNearestBackward");
+}
+
 // Debug hook (not in include/tfl.h): planes per CTA of the PCG sweep pipeline.
 extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
   if (!ctx) return 1;

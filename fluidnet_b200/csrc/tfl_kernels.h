@@ -105,5 +105,11 @@ void launch_upsample_nearest(const float* in, float* out, int nbf, int nz, int n
 void launch_blur_axis(const float* src, float* dst, int nbf, int nz, int ny, int nx, int axis, int rad, cudaStream_t st);
 void launch_signed_distance_field(const float* flags, float* dst, int nb, int nz, int ny, int nx, int rad,
                                   cudaStream_t st);
+void launch_velocity_divergence_backward(const float* flags, const float* go, float* grad_u, int nb, int nz, int ny,
+                                         int nx, int is3d, cudaStream_t st);
+void launch_velocity_update_backward(const float* flags, const float* go, float* grad_p, int nb, int nz, int ny, int nx,
+                                     int is3d, cudaStream_t st);
+void launch_upsample_nearest_backward(const float* go, float* gi, int nbf, int nz, int ny, int nx, int ratio,
+                                      cudaStream_t st);
 
 }  // namespace tfl

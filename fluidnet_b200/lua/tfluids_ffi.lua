@@ -58,6 +58,9 @@ int tfl_normalize_pressure_mean(tfl_ctx*, const tfl_grid* p, const tfl_grid* fla
 int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx*, int ratio, const tfl_grid* input, const tfl_grid* output);
 int tfl_rectangular_blur(tfl_ctx*, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst);
 int tfl_signed_distance_field(tfl_ctx*, const tfl_grid* flags, int search_rad, int is_3d, const tfl_grid* dst);
+int tfl_velocity_divergence_backward(tfl_ctx*, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* grad_output, const tfl_grid* grad_U);
+int tfl_velocity_update_backward(tfl_ctx*, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p, const tfl_grid* grad_output, const tfl_grid* grad_p);
+int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx*, int ratio, const tfl_grid* input, const tfl_grid* grad_output, const tfl_grid* grad_input);
 int tfl_empty_domain(tfl_ctx*, const tfl_grid* flags, int is_3d, int bnd);
 int tfl_flags_to_occupancy(tfl_ctx*, const tfl_grid* flags, const tfl_grid* occupancy, int64_t* bad_cells);
 int tfl_apply_bc(tfl_ctx*, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc);
@@ -227,6 +230,16 @@ end
 function tfluids.signedDistanceField(flags, searchRad, is3D, dst)          -- init.lua:604-614
   assert(searchRad > 0 and math.floor(searchRad) == searchRad, 'searchRad must be a positive, non-zero integer')
   check(lib.tfl_signed_distance_field(ctx, flags.c, searchRad, is3D and 1 or 0, dst.c))
+end
+
+function tfluids.velocityDivergenceBackward(U, flags, gradOutput, gradU)      -- init.lua:288-314
+  check(lib.tfl_velocity_divergence_backward(ctx, U.c, flags.c, gradOutput.c, gradU.c))
+end
+function tfluids.velocityUpdateBackward(U, flags, p, gradOutput, gradP)      -- init.lua:358-384
+  check(lib.tfl_velocity_update_backward(ctx, U.c, flags.c, p.c, gradOutput.c, gradP.c))
+end
+function tfluids.volumetricUpSamplingNearestBackward(ratio, input, gOut, gIn)   -- init.lua:623-627
+  check(lib.tfl_volumetric_up_sampling_nearest_backward(ctx, ratio, input.c, gOut.c, gIn.c))
 end
 
 -- The cutorch pair inside setConstVals (lib/simulate.lua:136-158) and U:clamp (:326).

@@ -337,6 +337,34 @@ def signedDistanceField(flags, searchRad, is3D, dst):
     c.check(c.lib.tfl_signed_distance_field(c.h, _grid(flags), int(searchRad), 1 if is3D else 0, _grid(dst)))
 
 
+def velocityDivergenceBackward(U, flags, gradOutput, gradU):
+    """init.lua:288-314."""
+    assert U.dim() == 5 and flags.dim() == 5 and gradOutput.dim() == 5 and gradU.dim() == 5, 'Dimension mismatch'
+    assert flags.size(1) == 1, 'flags is not scalar'
+    assert gradU.size() == U.size() and gradOutput.size() == flags.size(), 'Size mismatch'
+    assert all(t.is_contiguous() for t in (U, flags, gradOutput, gradU)), 'Input is not contiguous'
+    c = _ctx_for(U)
+    c.check(c.lib.tfl_velocity_divergence_backward(c.h, _grid(U), _grid(flags), _grid(gradOutput), _grid(gradU)))
+
+
+def velocityUpdateBackward(U, flags, p, gradOutput, gradP):
+    """init.lua:358-384."""
+    assert all(t.dim() == 5 for t in (U, flags, p, gradOutput, gradP)), 'Dimension mismatch'
+    assert flags.size(1) == 1, 'flags is not scalar'
+    assert gradP.size() == p.size() and gradOutput.size() == U.size(), 'Size mismatch'
+    assert all(t.is_contiguous() for t in (U, flags, p, gradOutput, gradP)), 'Input is not contiguous'
+    c = _ctx_for(U)
+    c.check(c.lib.tfl_velocity_update_backward(c.h, _grid(U), _grid(flags), _grid(p), _grid(gradOutput), _grid(gradP)))
+
+
+def volumetricUpSamplingNearestBackward(ratio, input, gradOutput, gradInput):
+    """init.lua:623-627."""
+    assert input.dim() == 5 and gradOutput.dim() == 5 and gradInput.dim() == 5
+    c = _ctx_for(input)
+    c.check(c.lib.tfl_volumetric_up_sampling_nearest_backward(c.h, int(ratio), _grid(input), _grid(gradOutput),
+                                                              _grid(gradInput)))
+
+
 def applyBC(x, invMask, bc):
     """x:cmul(invMask); x:add(bc) -- the cutorch pair in setConstVals (lib/simulate.lua:136-158)."""
     c = _ctx_for(x)

@@ -159,6 +159,19 @@ int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is
  * else the distance to the nearest obstacle cell within search_rad, capped at search_rad. */
 int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_rad, int is_3d,
                               const tfl_grid* dst);
+
+/* ---- backward passes (training side; forward operators above are what the simulation loop uses) ---- */
+/* tfluids.velocityDivergenceBackward (init.lua:288-314; generic/tfluids.cc:49-134): gradient of
+ * velocityDivergenceForward w.r.t. U.  U only supplies the shape, as in the reference. */
+int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
+                                     const tfl_grid* grad_output, const tfl_grid* grad_U);
+/* tfluids.velocityUpdateBackward (init.lua:358-384; generic/tfluids.cc:216-345): gradient of
+ * velocityUpdateForward w.r.t. p. */
+int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p,
+                                 const tfl_grid* grad_output, const tfl_grid* grad_p);
+/* tfluids.volumetricUpSamplingNearestBackward (init.lua:623-627; generic/tfluids.cc:563-635). */
+int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const tfl_grid* input,
+                                                const tfl_grid* grad_output, const tfl_grid* grad_input);
 /* tfluids.emptyDomain (init.lua:545-555; generic/tfluids.cu:314-353). */
 int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd);
 /* tfluids.flagsToOccupancy (init.lua:571-576; generic/tfluids.cu:355-401).  Cells that are

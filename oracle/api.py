@@ -217,6 +217,28 @@ class Oracle:
         return comp, sizes[:n].copy()
 
     # -- operators of tfluids/init.lua around the step ("next" rows) ----------------------------
+    def velocityDivergenceBackward(self, U, flags, gradOutput):
+        flags, go = _f32(flags), _f32(gradOutput)
+        d = _dims(flags, _is3d(U))
+        gU = np.empty_like(_f32(U))
+        self.lib.orc_velocity_divergence_backward(_ptr(flags), _ptr(go), _ptr(gU), C.byref(d))
+        return gU
+
+    def velocityUpdateBackward(self, U, flags, p, gradOutput):
+        flags, go = _f32(flags), _f32(gradOutput)
+        d = _dims(flags, _is3d(U))
+        gp = np.empty_like(flags)
+        self.lib.orc_velocity_update_backward(_ptr(flags), _ptr(go), _ptr(gp), C.byref(d))
+        return gp
+
+    def volumetricUpSamplingNearestBackward(self, ratio, x, gradOutput):
+        go = _f32(gradOutput)
+        nb, nf, nz, ny, nx = x.shape
+        gi = np.empty(x.shape, np.float32)
+        self.lib.orc_upsample_nearest_backward(_ptr(go), _ptr(gi), C.c_int(nb), C.c_int(nf), C.c_int(nz), C.c_int(ny),
+                                               C.c_int(nx), C.c_int(ratio))
+        return gi
+
     def volumetricUpSamplingNearestForward(self, ratio, x):
         x = _f32(x)
         nb, nf, nz, ny, nx = x.shape
@@ -450,6 +472,24 @@ class Reference(Oracle):
         inds = np.zeros(p.shape[:1] + p.shape[2:], np.int32)
         self._call("normalizePressureMean", p, _f32(flags), is3D, inds)
         return p
+
+    def velocityDivergenceBackward(self, U, flags, gradOutput):
+        U = _f32(U)
+        gU = np.full_like(U, np.float32(9.0))
+        self._call("velocityDivergenceBackward", U, _f32(flags), _f32(gradOutput), _is3d(U), gU)
+        return gU
+
+    def velocityUpdateBackward(self, U, flags, p, gradOutput):
+        U = _f32(U)
+        gp = np.full_like(_f32(flags), np.float32(9.0))
+        self._call("velocityUpdateBackward", U, _f32(flags), _f32(p), _f32(gradOutput), _is3d(U), gp)
+        return gp
+
+    def volumetricUpSamplingNearestBackward(self, ratio, x, gradOutput):
+        x = _f32(x)
+        gi = np.full_like(x, np.float32(9.0))
+        self._call("volumetricUpSamplingNearestBackward", ratio, x, _f32(gradOutput), gi)
+        return gi
 
     def findConnectedFluidComponents(self, flags, is3D, ibatch=0):
         flags = _f32(flags).copy()

@@ -1260,6 +1260,83 @@ void orc_normalize_pressure_mean(float* p, const float* flags, const orc_dims* d
 }
 
 /* ------------------------------------------------------------------------------------
+ * Backward operators of the two tfluids modules and of the nearest up-sampling (generic/tfluids.cc:49-134,
+ * 216-345, 563-635).  The reference scatters with OpenMP atomics; these are the equivalent gathers.  The
+ * divergence gradient has at most two terms per face (a - b is order-independent): bit-exact.  The
+ * velocity-update gradient sums up to nine terms in an unspecified order in the reference: compared at
+ * float-rounding tolerance.
+ * ---------------------------------------------------------------------------------- */
+static inline int interior(const orc_dims* d, int k, int j, int i) { return !on_border(d, k, j, i, 1); }
+
+void orc_velocity_divergence_backward(const float* flags, const float* grad_output, float* grad_u, const orc_dims* d) {
+  const long n = cells(d);
+  const int nc = nchan_vel(d);
+  for (int b = 0; b < d->nb; b++) {
+    int k, j, i;
+#pragma omp parallel for collapse(3) private(k, j, i) schedule(static)
+    for (k = 0; k < d->nz; k++) for (j = 0; j < d->ny; j++) for (i = 0; i < d->nx; i++) {
+      const long c = ((long)k * d->ny + j) * d->nx + i;
+      const int here = interior(d, k, j, i) && is_fluid(flags, d, b, k, j, i);
+      const int di[3] = {1, 0, 0}, dj[3] = {0, 1, 0}, dk[3] = {0, 0, 1};
+      for (int a = 0; a < nc; a++) {
+        float g = 0.0f;
+        if (here) g += grad_output[(long)b * n + c];
+        const int ii = i - di[a], jj = j - dj[a], kk = k - dk[a];
+        if (ii >= 0 && jj >= 0 && kk >= 0 && interior(d, kk, jj, ii) && is_fluid(flags, d, b, kk, jj, ii))
+          g -= grad_output[(long)b * n + ((long)kk * d->ny + jj) * d->nx + ii];
+        grad_u[((long)b * nc + a) * n + c] = g;
+      }
+    }
+  }
+}
+
+void orc_velocity_update_backward(const float* flags, const float* grad_output, float* grad_p, const orc_dims* d) {
+  const long n = cells(d);
+  const int nc = nchan_vel(d);
+  for (int b = 0; b < d->nb; b++) {
+    int k, j, i;
+#pragma omp parallel for collapse(3) private(k, j, i) schedule(static)
+    for (k = 0; k < d->nz; k++) for (j = 0; j < d->ny; j++) for (i = 0; i < d->nx; i++) {
+      const long c = ((long)k * d->ny + j) * d->nx + i;
+      const int di[3] = {1, 0, 0}, dj[3] = {0, 1, 0}, dk[3] = {0, 0, 1};
+      const int xf = is_fluid(flags, d, b, k, j, i);
+      float g = 0.0f;
+      if (interior(d, k, j, i) && xf) {                      /* this cell's own faces */
+        for (int a = 0; a < nc; a++)
+          if (is_fluid(flags, d, b, k - dk[a], j - dj[a], i - di[a])) g -= grad_output[((long)b * nc + a) * n + c];
+        for (int a = 0; a < nc; a++)
+          if (is_empty(flags, d, b, k - dk[a], j - dj[a], i - di[a])) g -= grad_output[((long)b * nc + a) * n + c];
+      }
+      if (xf) {                                              /* faces of the +x / +y / +z neighbours */
+        for (int a = 0; a < nc; a++) {
+          const int ii = i + di[a], jj = j + dj[a], kk = k + dk[a];
+          if (ii >= d->nx || jj >= d->ny || kk >= d->nz || !interior(d, kk, jj, ii)) continue;
+          const int yf = is_fluid(flags, d, b, kk, jj, ii);
+          const int ye = is_empty(flags, d, b, kk, jj, ii) && !is_outflow(flags, d, b, kk, jj, ii);
+          if (yf || ye) g += grad_output[((long)b * nc + a) * n + ((long)kk * d->ny + jj) * d->nx + ii];
+        }
+      }
+      grad_p[(long)b * n + c] = g;
+    }
+  }
+}
+
+/* volumetricUpSamplingNearestBackward, generic/tfluids.cc:563-635: sum of the ratio^3 window, z, y, x order. */
+void orc_upsample_nearest_backward(const float* grad_out, float* grad_in, int nb, int nf, int nz, int ny, int nx,
+                                   int ratio) {
+  const long oz = (long)nz * ratio, oy = (long)ny * ratio, ox = (long)nx * ratio;
+  long bf;
+#pragma omp parallel for schedule(static)
+  for (bf = 0; bf < (long)nb * nf; bf++)
+    for (long z = 0; z < nz; z++) for (long y = 0; y < ny; y++) for (long x = 0; x < nx; x++) {
+      float sum = 0;
+      for (int zu = 0; zu < ratio; zu++) for (int yu = 0; yu < ratio; yu++) for (int xu = 0; xu < ratio; xu++)
+        sum += grad_out[((bf * oz + z * ratio + zu) * oy + y * ratio + yu) * ox + x * ratio + xu];
+      grad_in[((bf * nz + z) * ny + y) * nx + x] = sum;
+    }
+}
+
+/* ------------------------------------------------------------------------------------
  * Lua-side pieces of the loop (lib/simulate.lua).
  * ---------------------------------------------------------------------------------- */
 /* x = x * invMask + bc  (setConstVals, lib/simulate.lua:136-158: cmul then add). */

@@ -87,3 +87,29 @@ def test_argument_errors(orc):
         tfluids.rectangularBlur(s, 0, True, torch.zeros_like(s))
     with pytest.raises(AssertionError, match="searchRad"):
         tfluids.signedDistanceField(f, 0, True, torch.zeros_like(f))
+
+
+@pytest.mark.parametrize("is3d", [True, False], ids=["3d", "2d"])
+def test_backward_operators(orc, is3d):
+    from fluidnet_b200 import synth, tfluids
+    rng = np.random.default_rng(3)
+    nx, ny, nz = (14, 12, 10) if is3d else (22, 18, 1)
+    fl = synth.make_flags(nx, ny, nz, is3d, nb=2, geometry=True, exotic=True)
+    U = synth.make_velocity(fl, is3d, amp=1.0)
+    go = rng.standard_normal(fl.shape).astype(np.float32)
+    want = orc.velocityDivergenceBackward(U, fl, go)
+    gU = torch.full(U.shape, 7.0, device="cuda")
+    tfluids.velocityDivergenceBackward(dev(U), dev(fl), dev(go), gU)
+    assert bits_equal(gU.cpu().numpy(), want), describe_diff(gU.cpu().numpy(), want)
+    goU = rng.standard_normal(U.shape).astype(np.float32)
+    p = rng.standard_normal(fl.shape).astype(np.float32)
+    want = orc.velocityUpdateBackward(U, fl, p, goU)
+    gp = torch.full(fl.shape, 7.0, device="cuda")
+    tfluids.velocityUpdateBackward(dev(U), dev(fl), dev(p), dev(goU), gp)
+    assert bits_equal(gp.cpu().numpy(), want), describe_diff(gp.cpu().numpy(), want)    # same fixed order as the oracle
+    x = rng.standard_normal((2, 3, 4, 5, 6)).astype(np.float32)
+    for ratio in (1, 2, 3):
+        g = rng.standard_normal((2, 3, 4 * ratio, 5 * ratio, 6 * ratio)).astype(np.float32)
+        gi = torch.full(x.shape, 7.0, device="cuda")
+        tfluids.volumetricUpSamplingNearestBackward(ratio, dev(x), dev(g), gi)
+        assert bits_equal(gi.cpu().numpy(), orc.volumetricUpSamplingNearestBackward(ratio, x, g))

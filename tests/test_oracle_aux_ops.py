@@ -69,3 +69,47 @@ def test_normalize_pressure_mean(orc, ref, is3d):
     comp, sizes = orc.findConnectedFluidComponents(flags, is3d, 0)
     for ic in range(len(sizes)):
         assert abs(p1[0, 0][comp == ic].astype(np.float64).mean()) < 1e-5
+
+
+@pytest.mark.parametrize("is3d", [True, False])
+def test_backward_operators(orc, ref, is3d):
+    """velocityDivergenceBackward (bit-exact: at most two terms per face), velocityUpdateBackward (the
+    reference sums up to nine terms with OpenMP atomics: float-rounding tolerance),
+    volumetricUpSamplingNearestBackward (bit-exact)."""
+    from fluidnet_b200 import synth
+    rng = np.random.default_rng(3)
+    nx, ny, nz = (14, 12, 10) if is3d else (22, 18, 1)
+    fl = synth.make_flags(nx, ny, nz, is3d, nb=2, geometry=True, exotic=True)
+    U = synth.make_velocity(fl, is3d, amp=1.0)
+    go = rng.standard_normal(fl.shape).astype(np.float32)
+    a, b = orc.velocityDivergenceBackward(U, fl, go), ref.velocityDivergenceBackward(U, fl, go)
+    assert bits_equal(a, b), describe_diff(a, b)
+    goU = rng.standard_normal(U.shape).astype(np.float32)
+    p = rng.standard_normal(fl.shape).astype(np.float32)
+    a, b = orc.velocityUpdateBackward(U, fl, p, goU), ref.velocityUpdateBackward(U, fl, p, goU)
+    assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    x = rng.standard_normal((2, 3, 4, 5, 6)).astype(np.float32)
+    for ratio in (1, 2, 3):
+        g = rng.standard_normal((2, 3, 4 * ratio, 5 * ratio, 6 * ratio)).astype(np.float32)
+        assert bits_equal(orc.volumetricUpSamplingNearestBackward(ratio, x, g),
+                          ref.volumetricUpSamplingNearestBackward(ratio, x, g))
+
+
+def test_backward_is_the_adjoint(orc):
+    """<J v, w> == <v, J^T w> for the two linear forward operators (an independent check of the gathers)."""
+    from fluidnet_b200 import synth
+    rng = np.random.default_rng(4)
+    fl = synth.make_flags(12, 11, 10, True, nb=1, geometry=True, exotic=True)
+    U = rng.standard_normal((1, 3, 10, 11, 12)).astype(np.float32)
+    w = rng.standard_normal(fl.shape).astype(np.float32)
+    lhs = float((orc.velocityDivergenceForward(U, fl).astype(np.float64) * w).sum())
+    rhs = float((U.astype(np.float64) * orc.velocityDivergenceBackward(U, fl, w)).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+    p = rng.standard_normal(fl.shape).astype(np.float32)
+    wU = rng.standard_normal(U.shape).astype(np.float32)
+    U0 = np.zeros_like(U)
+    upd = U0.copy()
+    orc.velocityUpdateForward(upd, fl, p)                     # linear in p for U = 0
+    lhs = float((upd.astype(np.float64) * wU).sum())
+    rhs = float((p.astype(np.float64) * orc.velocityUpdateBackward(U0, fl, p, wU)).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
