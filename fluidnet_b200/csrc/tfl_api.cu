@@ -764,7 +764,6 @@ int tfl_debug_cnn_use_ts(tfl_cnn* m, int on) { if (m) m->use_ts = on; return 0; 
 // Undocumented debugging hook (not in tfl.h): per-CTA phase timestamps of the tensor-core conv.
 int tfl_debug_conv_timestamps(void* dev_buf) { conv_tc_set_debug((long long*)dev_buf); return 0; }
 int tfl_debug_conv_ts_counters(void* dev_buf) { conv_ts_set_debug((long long*)dev_buf); return 0; }
-int tfl_debug_conv_ts_variant(int v) { conv_ts_set_variant(v); return 0; }
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   if (!m) return;

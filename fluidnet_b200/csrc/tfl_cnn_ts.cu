@@ -378,7 +378,6 @@ void launch_ts(const float4* in, float4* out, float* p_net, const float* wB, con
 }  // namespace
 
 void conv_ts_set_debug(long long* dev_buf) { cudaMemcpyToSymbol(g_ts_dbg, &dev_buf, sizeof(dev_buf)); }
-void conv_ts_set_variant(int) {}
 
 int conv_ts_b_floats() { return kGroups * 2 * kNB * 4; }
 

@@ -10,8 +10,6 @@ p = torch.zeros_like(flags)
 gm = make_gpu_model(synth.make_model(True))
 lib = tfluids.context().lib
 for variant in (0,):
-  lib.tfl_debug_conv_ts_variant(variant)
-  print('variant', variant)
   for _ in range(2):
     gm.forward((p, U, flags))
   torch.cuda.synchronize()
@@ -20,7 +18,6 @@ for variant in (0,):
   for _ in range(10): gm.forward((p, U, flags))
   b.record(); torch.cuda.synchronize()
   print('  model:forward %.3f ms' % (a.elapsed_time(b) / 10))
-lib.tfl_debug_conv_ts_variant(0)
 buf = torch.zeros(8 * 1024, dtype=torch.int64, device="cuda")
 lib.tfl_debug_conv_ts_counters(C.c_void_p(buf.data_ptr()))
 gm.forward((p, U, flags))
