@@ -52,6 +52,14 @@ struct tfl_cnn {
   std::vector<float*> w;     // device, [cin][tap][cout]
   std::vector<float*> b;     // device, [cout]
   int max_c = 0;
+  // per-layer extras of the 'tog' / 'yang' graphs (lib/model.lua:164-239): the convolution emits
+  // cout * up^d channels that a pixel shuffle turns into cout channels at `up` times the resolution, a
+  // pooling of size `pool` follows the non-linearity.  plain = every pool / up is 1 and the non-linearity is ReLU.
+  std::vector<int> pool, up;
+  int pool_is_max = 0;
+  int nonlin = 1;            // 1 ReLU, 2 sigmoid (activation codes of tfl_cnn.cu)
+  bool plain = true;
+  double max_rel = 0.0;      // largest channels x (cells relative to the input grid) of any stage
   // tensor-core path (3-D 'default' architecture only)
   int mode = 0;              // 0 fp32 FMA, 1 TF32 tensor cores, 2 3xTF32 tensor cores
   bool tc_ok = false;
@@ -694,14 +702,38 @@ int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
 int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
                    const int32_t* ksize, const float* const* weights, const float* const* biases,
                    tfl_cnn** out) {
+  return tfl_cnn_create_graph(ctx, is_3d, n_layers, cin, cout, ksize, nullptr, nullptr, 0, 0, weights, biases, out);
+}
+
+int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout_logical,
+                         const int32_t* ksize, const int32_t* pool, const int32_t* up, int pool_is_max,
+                         int nonlin_sigmoid, const float* const* weights, const float* const* biases,
+                         tfl_cnn** out) {
   if (!out || n_layers < 1) return fail(ctx, "cnn: bad arguments");
+  // Channels the convolution of layer l really emits: cout * up^d (ConvolutionUpsample, model_utils.lua:74-76).
+  std::vector<int32_t> cout_conv(n_layers);
+  bool plain = !nonlin_sigmoid;
+  for (int l = 0; l < n_layers; l++) {
+    const int u = up ? up[l] : 1, pl = pool ? pool[l] : 1;
+    if (u < 1 || pl < 1) return fail(ctx, "cnn: pooling / upsampling sizes must be >= 1");
+    if (u > 1 && pl > 1) return fail(ctx, "Pooling and upsampling in the same layer!");          // model.lua:326
+    if (l == n_layers - 1 && pl != 1) return fail(ctx, "Pooling is not allowed in the last layer");  // model.lua:245
+    cout_conv[l] = cout_logical[l] * u * u * (is_3d ? u : 1);
+    if (u != 1 || pl != 1) plain = false;
+  }
+  const int32_t* cout = cout_conv.data();
+  if (cout_logical[n_layers - 1] != 1) return fail(ctx, "Last layer osize must be 1 (pressure)");   // model.lua:244
   if (cin[0] != 3) return fail(ctx, "cnn: the first layer must take 3 channels (pDiv, div, occupancy)");
-  if (cout[n_layers - 1] != 1) return fail(ctx, "Last layer osize must be 1 (pressure)");   // model.lua:244
   tfl_cnn* m = new tfl_cnn();
+  m->plain = plain;
+  m->pool_is_max = pool_is_max ? 1 : 0;
+  m->nonlin = nonlin_sigmoid ? 2 : 1;
   m->is3d = is_3d ? 1 : 0;
   m->n_layers = n_layers;
   for (int l = 0; l < n_layers; l++) {
-    if (l > 0 && cin[l] != cout[l - 1]) { delete m; return fail(ctx, "cnn: channel mismatch at layer %d", l); }
+    if (l > 0 && cin[l] != cout_logical[l - 1]) { delete m; return fail(ctx, "cnn: channel mismatch at layer %d", l); }
+    m->pool.push_back(pool ? pool[l] : 1);
+    m->up.push_back(up ? up[l] : 1);
     if (ksize[l] % 2 != 1) { delete m; return fail(ctx, "convolution size must be odd"); }   // model_utils.lua:70
     const int kz = is_3d ? ksize[l] : 1;
     const int taps = kz * ksize[l] * ksize[l];
@@ -719,9 +751,22 @@ int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, co
     m->w.push_back(dw); m->b.push_back(db);
     if (cout[l] > m->max_c) m->max_c = cout[l];
   }
+  {   // largest activation of the graph, in channels x cells-of-the-input-grid
+    double rel = 1.0;
+    m->max_rel = 3.0;
+    for (int l = 0; l < n_layers; l++) {
+      m->max_rel = std::max(m->max_rel, rel * cout[l]);                          // convolution output
+      const int u = m->up[l], pl = m->pool[l];
+      rel *= (double)u * u * (is_3d ? u : 1);
+      m->max_rel = std::max(m->max_rel, rel * cout_logical[l]);                  // after the pixel shuffle
+      rel /= (double)pl * pl * (is_3d ? pl : 1);
+    }
+    if (rel != 1.0) { tfl_cnn_destroy(ctx, m); return fail(ctx, "cnn: pooling and upsampling do not return to the input resolution"); }
+    if ((double)m->max_c < m->max_rel) m->max_c = (int)std::ceil(m->max_rel);
+  }
   // Tensor-core eligibility: the 3-D 'default' graph (lib/model.lua:219-226).
   static const int want[5][3] = {{3, 8, 3}, {8, 8, 3}, {8, 8, 3}, {8, 8, 1}, {8, 1, 1}};
-  m->tc_ok = is_3d && n_layers == 5;
+  m->tc_ok = plain && is_3d && n_layers == 5;
   for (int l = 0; m->tc_ok && l < 5; l++)
     m->tc_ok = cin[l] == want[l][0] && cout[l] == want[l][1] && ksize[l] == want[l][2];
   if (m->tc_ok) {
@@ -820,7 +865,7 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   auto take = [&](size_t bytes) { char* p = scratch + off; off = (off + bytes + 255) & ~(size_t)255; return p; };
   float* U1 = (float*)take(cells * 4 * g.nc);
   float* x0 = (float*)take(cells * 4 * 3);
-  float* actA = (float*)take(cells * 4 * m->max_c);
+  float* actA = (float*)take(cells * 4 * m->max_c);      // max_c covers max_rel (set at creation)
   float* actB = (float*)take(cells * 4 * m->max_c);
   float* scale = (float*)take(sizeof(float) * g.nb);
   double* sums = ctx->dscratch + 64;
@@ -842,14 +887,57 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
   launch_cnn_inputs(p_div, U1, flags, scale, x0, g, st);
   ctx->launches += 3;
   const float* in = x0;
-  float* bufs[2] = {actA, actB};
-  for (int l = 0; l < m->n_layers; l++) {
-    float* o = bufs[l & 1];
-    const int relu = (l < m->n_layers - 1) ? 1 : 0;
-    if (launch_conv_direct(in, o, m->w[l], m->b[l], m->cin[l], m->cout[l], m->ks[l], relu, g, st) < 0)
-      return fail(ctx, "cnn: unsupported layer shape cout=%d k=%d", m->cout[l], m->ks[l]);
-    ctx->launches += 1;
-    in = o;
+  if (m->plain) {
+    float* bufs[2] = {actA, actB};
+    for (int l = 0; l < m->n_layers; l++) {
+      float* o = bufs[l & 1];
+      const int act = (l < m->n_layers - 1) ? 1 : 0;
+      if (launch_conv_direct(in, o, m->w[l], m->b[l], m->cin[l], m->cout[l], m->ks[l], act, g, st) < 0)
+        return fail(ctx, "cnn: unsupported layer shape cout=%d k=%d", m->cout[l], m->ks[l]);
+      ctx->launches += 1;
+      in = o;
+    }
+  } else {
+    // 'tog' / 'yang' graphs: conv (+ pixel shuffle) -> non-linearity -> pooling, layer by layer, on grids
+    // whose resolution follows the pooling / upsampling sizes (lib/model.lua:262-340, single bank).
+    if (ctx->slab) return fail(ctx, "cnn: pooled / upsampled graphs run on whole grids only");
+    float* bufs[3] = {actA, actB, (float*)take((size_t)((double)cells * m->max_rel + 64) * 4)};
+    auto other = [&](const float* a, const float* b2) {
+      for (float* c : bufs) if (c != a && c != b2) return c;
+      return bufs[0];
+    };
+    Geo gl = g;
+    for (int l = 0; l < m->n_layers; l++) {
+      const int u = m->up[l], pl = m->pool[l];
+      const int act = (l < m->n_layers - 1) ? m->nonlin : 0;     // element-wise: commutes with the shuffle
+      float* o = other(in, nullptr);
+      if (launch_conv_direct(in, o, m->w[l], m->b[l], m->cin[l], m->cout[l], m->ks[l], act, gl, st) < 0)
+        return fail(ctx, "cnn: unsupported layer shape cout=%d k=%d", m->cout[l], m->ks[l]);
+      ctx->launches += 1;
+      const float* cur = o;
+      int chans = m->cout[l];
+      if (u > 1) {
+        chans = m->cout[l] / (u * u * (gl.is3d ? u : 1));
+        float* sh = other(cur, nullptr);
+        launch_pixel_shuffle(cur, sh, gl.nb, chans, gl.nz, gl.ny, gl.nx, u, gl.is3d, st);
+        ctx->launches += 1;
+        gl.nx *= u; gl.ny *= u; if (gl.is3d) gl.nz *= u;
+        cur = sh;
+      }
+      if (pl > 1) {
+        if (gl.nx % pl || gl.ny % pl || (gl.is3d && gl.nz % pl))
+          return fail(ctx, "cnn: grid %dx%dx%d is not divisible by the pooling size %d", gl.nx, gl.ny, gl.nz, pl);
+        float* po = other(cur, nullptr);
+        launch_pool(cur, po, gl.nb * chans, gl.nz, gl.ny, gl.nx, pl, gl.is3d, m->pool_is_max, st);
+        ctx->launches += 1;
+        gl.nx /= pl; gl.ny /= pl; if (gl.is3d) gl.nz /= pl;
+        cur = po;
+      }
+      gl.n = (long long)gl.nx * gl.ny * gl.nz;
+      gl.gnz = gl.nz; gl.zlo = 0; gl.zhi = gl.nz;
+      in = cur;
+    }
+    if (gl.nx != g.nx || gl.ny != g.ny || gl.nz != g.nz) return fail(ctx, "cnn: graph does not return to the input resolution");
   }
   launch_cnn_finish(in, U1, flags, scale, p_out, U_out, g, st);
   ctx->launches += 1;
@@ -859,7 +947,9 @@ static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const 
 
 static size_t cnn_scratch_bytes(const tfl_cnn* m, const Geo& g) {
   const size_t cells = (size_t)g.n * g.nb;
-  return cells * 4 * (g.nc + 3 + 2 * (size_t)m->max_c) + 4 * g.nb + 8 * 256;
+  size_t bytes = cells * 4 * (g.nc + 3 + 2 * (size_t)m->max_c) + 4 * g.nb + 8 * 256;
+  if (!m->plain) bytes += (size_t)((double)cells * m->max_rel + 64) * 4 + 256;     // third rotating buffer
+  return bytes;
 }
 
 int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_grid* U_div,

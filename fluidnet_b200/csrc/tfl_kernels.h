@@ -74,8 +74,13 @@ void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* 
 // ---- tfl_cnn.cu ----
 // Generic direct convolution (fp32 FMA): in [b][cin][z][y][x] -> out [b][cout][z][y][x].
 // wdev: device weights re-laid out as [cin][tap][cout_pad], bias [cout].
+// act: 0 none, 1 ReLU, 2 sigmoid.
 int launch_conv_direct(const float* in, float* out, const float* wdev, const float* bdev, int cin, int cout,
-                       int ksize, int relu, const Geo& g, cudaStream_t st);
+                       int ksize, int act, const Geo& g, cudaStream_t st);
+void launch_pool(const float* in, float* out, int nbc, int nz, int ny, int nx, int p, int is3d, int is_max,
+                 cudaStream_t st);
+void launch_pixel_shuffle(const float* in, float* out, int nb, int n_out, int nz, int ny, int nx, int s, int is3d,
+                          cudaStream_t st);
 
 // ---- tfl_pcg.cu: matrix-free PCG pressure solve ----
 struct PcgScratch {            // owned by the context, grow-only

@@ -70,6 +70,9 @@ int tfl_cnn_create(tfl_ctx*, int is_3d, int n_layers, const int32_t* cin, const 
 void tfl_cnn_destroy(tfl_ctx*, tfl_cnn*);
 int tfl_cnn_project(tfl_ctx*, tfl_cnn*, const tfl_grid* p_div, const tfl_grid* U_div, const tfl_grid* flags,
                     const tfl_grid* p_out, const tfl_grid* U_out, float threshold, float* scale_out);
+int tfl_cnn_create_graph(tfl_ctx*, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout, const int32_t* ksize,
+                         const int32_t* pool, const int32_t* up, int pool_is_max, int nonlin_sigmoid,
+                         const float* const* weights, const float* const* biases, tfl_cnn** out);
 int tfl_simulate_step(tfl_ctx*, const tfl_state*, const tfl_mconf*, tfl_cnn*);
 ]]
 

@@ -22,16 +22,25 @@ def default_layers(is3D):
 
 
 class ProjectionModel:
-    def __init__(self, layers, is3D, device=None, normalizeInputThreshold=1e-5):
-        """layers: [(weight ndarray [cout][cin][kz][ky][kx], bias ndarray [cout]), ...]"""
+    def __init__(self, layers, is3D, device=None, normalizeInputThreshold=1e-5, pool=None, up=None,
+                 poolType="avg", nonlinType="relu"):
+        """layers: [(weight ndarray [cout * up^d][cin][kz][ky][kx], bias ndarray [cout * up^d]), ...]
+        pool / up: per-layer pooling and ConvolutionUpsample sizes of the 'tog' graph (lib/model.lua:164-226),
+        None = all 1 ('default', 'yang'); poolType 'avg' | 'max'; nonlinType 'relu' | 'sigmoid'."""
         self.is3D = bool(is3D)
         self.threshold = float(normalizeInputThreshold)
         self.ctx = tfluids.context(device)
         n = len(layers)
+        pool = [1] * n if pool is None else [int(v) for v in pool]
+        up = [1] * n if up is None else [int(v) for v in up]
+        assert len(pool) == n and len(up) == n
+        assert poolType in ("avg", "max") and nonlinType in ("relu", "sigmoid")
         self._keep = []
         cin = (C.c_int32 * n)()
         cout = (C.c_int32 * n)()
         ks = (C.c_int32 * n)()
+        cpool = (C.c_int32 * n)(*pool)
+        cup = (C.c_int32 * n)(*up)
         wp = (C.POINTER(C.c_float) * n)()
         bp = (C.POINTER(C.c_float) * n)()
         for l, (w, b) in enumerate(layers):
@@ -39,13 +48,16 @@ class ProjectionModel:
             b = np.ascontiguousarray(b, dtype=np.float32)
             assert w.ndim == 5 and b.ndim == 1 and b.shape[0] == w.shape[0]
             assert w.shape[3] == w.shape[4] and w.shape[2] == (w.shape[4] if is3D else 1)
+            fan = up[l] ** (3 if is3D else 2)
+            assert w.shape[0] % fan == 0, "ConvolutionUpsample layer: cout must be a multiple of up^d"
             self._keep += [w, b]
-            cout[l], cin[l], ks[l] = w.shape[0], w.shape[1], w.shape[4]
+            cout[l], cin[l], ks[l] = w.shape[0] // fan, w.shape[1], w.shape[4]
             wp[l] = w.ctypes.data_as(C.POINTER(C.c_float))
             bp[l] = b.ctypes.data_as(C.POINTER(C.c_float))
         h = C.c_void_p()
-        self.ctx.check(self.ctx.lib.tfl_cnn_create(self.ctx.h, 1 if is3D else 0, n, cin, cout, ks, wp, bp,
-                                                   C.byref(h)))
+        self.ctx.check(self.ctx.lib.tfl_cnn_create_graph(self.ctx.h, 1 if is3D else 0, n, cin, cout, ks, cpool, cup,
+                                                         1 if poolType == "max" else 0,
+                                                         1 if nonlinType == "sigmoid" else 0, wp, bp, C.byref(h)))
         self.h = h
         self.last_scale = None
 

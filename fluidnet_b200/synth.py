@@ -81,21 +81,41 @@ def make_density(flags, seed=1235):
     return np.ascontiguousarray(d)
 
 
-def make_model(is3d=True, seed=4321):
-    """Random-init weights of the reference 'default' architecture
-    (torch/lib/model.lua:179-186 2-D, :219-226 3-D), Torch `reset` convention
-    uniform +-1/sqrt(fan_in). Inputs: pDiv, div, occupancy (lib/default_conf.lua:76-81)."""
+def make_model(is3d=True, seed=4321, model_type="default"):
+    """Random-init weights of a reference architecture (torch/lib/model.lua:164-226: 'default', 'tog',
+    'yang'), Torch `reset` convention uniform +-1/sqrt(fan_in).  Inputs: pDiv, div, occupancy
+    (lib/default_conf.lua:76-81).  'tog' layers carry pooling / ConvolutionUpsample sizes: the weights of
+    an upsampling layer have cout * up^d output channels."""
     rs = np.random.RandomState(seed)
-    if is3d:
-        spec = [(3, 8, 3), (8, 8, 3), (8, 8, 3), (8, 8, 1), (8, 1, 1)]
+    extra = {}
+    if model_type == "default":
+        osize, ksize = ([8, 8, 8, 8, 1], [3, 3, 3, 1, 1]) if is3d else ([16, 16, 16, 16, 1], [3, 3, 3, 3, 1])
+        psize = usize = [1] * 5
+    elif model_type == "tog":
+        if is3d:
+            osize, ksize = [16, 16, 16, 16, 32, 32, 1], [3, 3, 3, 3, 1, 1, 3]
+            psize, usize = [2, 2, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 2, 2]
+        else:
+            osize, ksize = [16, 32, 32, 64, 64, 32, 1], [5, 5, 5, 5, 1, 1, 3]
+            psize, usize = [2, 1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 2]
+        extra = {"pool": psize, "up": usize, "poolType": "avg"}
+    elif model_type == "yang":
+        osize, ksize = [6, 6, 6, 1], [3, 1, 1, 1]
+        psize = usize = [1] * 4
+        extra = {"nonlinType": "sigmoid"}
     else:
-        spec = [(3, 16, 3), (16, 16, 3), (16, 16, 3), (16, 16, 3), (16, 1, 1)]
+        raise ValueError(model_type)
     layers = []
-    for cin, cout, k in spec:
+    cin = 3
+    for cout, k, u in zip(osize, ksize, usize):
         kz = k if is3d else 1
         fan_in = cin * kz * k * k
         bound = 1.0 / np.sqrt(fan_in)
-        w = ((rs.rand(cout, cin, kz, k, k) * 2 - 1) * bound).astype(np.float32)
-        b = ((rs.rand(cout) * 2 - 1) * bound).astype(np.float32)
+        ct = cout * u ** (3 if is3d else 2)
+        w = ((rs.rand(ct, cin, kz, k, k) * 2 - 1) * bound).astype(np.float32)
+        b = ((rs.rand(ct) * 2 - 1) * bound).astype(np.float32)
         layers.append((np.ascontiguousarray(w), np.ascontiguousarray(b)))
-    return {"is3D": is3d, "layers": layers}
+        cin = cout
+    out = {"is3D": is3d, "layers": layers}
+    out.update(extra)
+    return out

@@ -195,6 +195,16 @@ int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi);
 int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
                    const int32_t* ksize, const float* const* weights, const float* const* biases,
                    tfl_cnn** out);
+/* The other single-bank graphs of lib/model.lua:164-239 ('tog', 'yang'): layer l is
+ *   convolution cin[l] -> cout[l] * up[l]^d channels (kernel ksize[l], zero padding), the pixel shuffle of
+ *   nn.{Spatial,Volumetric}ConvolutionUpsample when up[l] > 1, the non-linearity (all layers but the
+ *   last; ReLU, or sigmoid when nonlin_sigmoid), then cudnn average / max pooling of size pool[l].
+ * weights[l]: [cout[l] * up[l]^d][cin[l]][kz][ky][kx].  pool / up may be NULL (all 1: tfl_cnn_create).
+ * These graphs run on the fp32 path; the tensor-core kernels cover the 3-D 'default' graph. */
+int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
+                         const int32_t* ksize, const int32_t* pool, const int32_t* up, int pool_is_max,
+                         int nonlin_sigmoid, const float* const* weights, const float* const* biases,
+                         tfl_cnn** out);
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* cnn);
 /* Arithmetic of the convolution stack: 0 = fp32 FMA on the CUDA cores; 1 = TF32 tensor cores
  * (tcgen05, fp32 accumulate); 2 = 3xTF32 tensor cores (error-compensated split, fp32-class

@@ -583,8 +583,37 @@ def model_forward(be, model, pDiv, UDiv, flags, threshold=1e-5):
     occ = be.flagsToOccupancy(flags)                                    # :144-147
     x = np.ascontiguousarray(np.concatenate([pS, divS, occ], axis=1))   # :134-150
     nl = len(model["layers"])
+    pool = model.get("pool") or [1] * nl                                # 'tog' graphs, model.lua:164-226
+    up = model.get("up") or [1] * nl
+    sigmoid = model.get("nonlinType", "relu") == "sigmoid"
     for li, (w, bias) in enumerate(model["layers"]):
-        x = be.conv(x, w, bias, is3d, relu=(li < nl - 1))
+        plain = up[li] == 1 and pool[li] == 1 and not sigmoid
+        x = be.conv(x, w, bias, is3d, relu=(plain and li < nl - 1))
+        if plain:
+            continue
+        if up[li] > 1:                                                  # *_convolution_upsample.lua updateOutput
+            s_ = up[li]
+            b_, ct, z_, y_, x_ = x.shape
+            if is3d:
+                no = ct // s_ ** 3
+                x = x.reshape(b_, no, s_, s_, s_, z_, y_, x_).transpose(0, 1, 5, 2, 6, 3, 7, 4)
+                x = np.ascontiguousarray(x).reshape(b_, no, z_ * s_, y_ * s_, x_ * s_)
+            else:
+                no = ct // s_ ** 2
+                x = x.reshape(b_, no, s_, s_, z_, y_, x_).transpose(0, 1, 4, 5, 2, 6, 3)
+                x = np.ascontiguousarray(x).reshape(b_, no, z_, y_ * s_, x_ * s_)
+        if li < nl - 1:                                                 # addNonlinearity
+            x = (1.0 / (1.0 + np.exp(-x.astype(np.float64)))).astype(np.float32) if sigmoid else np.maximum(x, 0)
+        if pool[li] > 1:                                                # addPooling (cudnn avg / max)
+            q = pool[li]
+            b_, c_, z_, y_, x_ = x.shape
+            qz = q if is3d else 1
+            v = x.reshape(b_, c_, z_ // qz, qz, y_ // q, q, x_ // q, q)
+            if model.get("poolType", "avg") == "max":
+                x = v.max(axis=(3, 5, 7))
+            else:
+                x = (v.astype(np.float64).sum(axis=(3, 5, 7)) / (qz * q * q)).astype(np.float32)
+        x = np.ascontiguousarray(x, np.float32)
     p = x
     U2 = np.ascontiguousarray(US.copy())
     be.velocityUpdateForward(U2, flags, p)                              # :380

@@ -115,7 +115,10 @@ class GpuBackend:
 
 
 def make_gpu_model(model_np, threshold=1e-5):
-    return fmodel.ProjectionModel(model_np["layers"], model_np["is3D"], normalizeInputThreshold=threshold)
+    return fmodel.ProjectionModel(model_np["layers"], model_np["is3D"], normalizeInputThreshold=threshold,
+                                  pool=model_np.get("pool"), up=model_np.get("up"),
+                                  poolType=model_np.get("poolType", "avg"),
+                                  nonlinType=model_np.get("nonlinType", "relu"))
 
 
 def batch_to_gpu(batch):

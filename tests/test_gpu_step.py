@@ -192,6 +192,44 @@ def test_trained_reference_model_2d(orc):
             close(gb[k].cpu().numpy(), batch[k], 2e-5 * (step + 1) * 5, "step %d %s" % (step, k))
 
 
+@pytest.mark.parametrize("is3d,n,model_type,pool_type", [(False, 48, "tog", "avg"), (True, 24, "tog", "avg"),
+                                                          (True, 16, "tog", "max"), (False, 40, "yang", "avg"),
+                                                          (True, 20, "yang", "avg")],
+                         ids=["2d-tog", "3d-tog", "3d-tog-max", "2d-yang", "3d-yang"])
+def test_cnn_model_graphs(orc, is3d, n, model_type, pool_type):
+    """The other single-bank graphs of lib/model.lua:164-226: 'tog' (pooling, ConvolutionUpsample pixel
+    shuffles, 5x5 / 1x1 / 256-channel convolutions) and 'yang' (sigmoid), model:forward against the oracle
+    (whose graph semantics are pinned on torch.nn.functional, tests/test_oracle_model_graph.py)."""
+    from gpu_backend import make_gpu_model
+    batch = make_batch(n, is3d, plume=False)
+    mnp = synth.make_model(is3d, model_type=model_type)
+    if model_type == "tog":
+        mnp["poolType"] = pool_type
+    p0 = (synth.make_density(batch["flags"], seed=77) - np.float32(0.5)) * np.float32(0.1)
+    wp, wU, wscale = oracle.model_forward(orc, mnp, p0, batch["UDiv"], batch["flags"])
+    gm = make_gpu_model(mnp)
+    assert gm.get_mode() == "fp32"
+    gp, gU = gm.forward((torch.from_numpy(p0).cuda(), torch.from_numpy(batch["UDiv"]).cuda(),
+                         torch.from_numpy(batch["flags"]).cuda()), return_scale=True)
+    assert abs(gm.last_scale[0] - wscale[0]) <= 1e-5 * wscale[0]
+    close(gp.cpu().numpy(), wp, 2e-5, "p")
+    close(gU.cpu().numpy(), wU, 2e-5, "U")
+
+
+def test_cnn_graph_argument_errors():
+    from fluidnet_b200 import model as fmodel
+    from fluidnet_b200._lib import TflError
+    m = synth.make_model(True, model_type="tog")
+    with pytest.raises(TflError, match="same layer"):
+        fmodel.ProjectionModel(m["layers"], True, pool=[2, 2, 1, 1, 1, 2, 1], up=m["up"])
+    with pytest.raises(TflError, match="input resolution"):
+        fmodel.ProjectionModel(m["layers"], True, pool=[2, 1, 1, 1, 1, 1, 1], up=m["up"])
+    gm = fmodel.ProjectionModel(m["layers"], True, pool=m["pool"], up=m["up"])
+    f = torch.ones(1, 1, 6, 8, 8, device="cuda")               # 6 is not divisible by the two 2x poolings
+    with pytest.raises(TflError, match="divisible"):
+        gm.forward((torch.zeros_like(f), torch.zeros(1, 3, 6, 8, 8, device="cuda"), f))
+
+
 def test_full_size_properties():
     """BASELINE-size (128^3) checks that do not need the CPU oracle: the Jacobi-projected
     velocity is (nearly) divergence free, the obstacle faces stay exactly zero, advection of
