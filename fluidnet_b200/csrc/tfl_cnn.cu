@@ -153,7 +153,7 @@ __global__ void k_pixel_shuffle(const float* __restrict__ in, float* __restrict_
 }
 
 template <int COUT, int KS, bool IS3D>
-static void conv_launch(const float* in, float* out, const float* w, const float* b, int cin, int act,
+static bool conv_launch(const float* in, float* out, const float* w, const float* b, int cin, int act,
                         const Geo& g, cudaStream_t st) {
   const int nzr = g.zhi - g.zlo;
   dim3 block = IS3D ? dim3(32, 4, 2) : dim3(32, 8, 1);
@@ -161,16 +161,29 @@ static void conv_launch(const float* in, float* out, const float* w, const float
             ((long long)g.nb * nzr + block.z - 1) / block.z);
   constexpr int KZ = IS3D ? KS : 1;
   const size_t smem = sizeof(float) * cin * KZ * KS * KS * COUT;
+  if (smem > 200 * 1024) return false;             // weights do not fit shared memory: generic kernel
+  if (smem > 48 * 1024) {
+    static size_t allowed = 0;                     // per instantiation
+    if (smem > allowed) {
+      if (cudaFuncSetAttribute(k_conv_direct<COUT, KS, IS3D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      allowed = smem;
+    }
+  }
   k_conv_direct<COUT, KS, IS3D><<<grid, block, smem, st>>>(in, out, w, b, cin, act, g);
+  return true;
 }
 
 int launch_conv_direct(const float* in, float* out, const float* wdev, const float* bdev, int cin, int cout,
                        int ksize, int act, const Geo& g, cudaStream_t st) {
 #define TFL_CONV_CASE(CO, KS_)                                                        \
   if (cout == CO && ksize == KS_) {                                                   \
-    if (g.is3d) conv_launch<CO, KS_, true>(in, out, wdev, bdev, cin, act, g, st);     \
-    else conv_launch<CO, KS_, false>(in, out, wdev, bdev, cin, act, g, st);           \
-    return 1;                                                                         \
+    const bool ok_ = g.is3d ? conv_launch<CO, KS_, true>(in, out, wdev, bdev, cin, act, g, st)    \
+                            : conv_launch<CO, KS_, false>(in, out, wdev, bdev, cin, act, g, st);  \
+    if (ok_) return 1;                                                                \
   }
   TFL_CONV_CASE(8, 3) TFL_CONV_CASE(8, 1) TFL_CONV_CASE(1, 1) TFL_CONV_CASE(16, 3) TFL_CONV_CASE(16, 1)
   TFL_CONV_CASE(1, 3) TFL_CONV_CASE(6, 3) TFL_CONV_CASE(6, 1) TFL_CONV_CASE(32, 1) TFL_CONV_CASE(16, 5)
