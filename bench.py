@@ -94,14 +94,18 @@ class ClockSampler(threading.Thread):
 
 
 def make_problem(n=N_GRID):
-    from fluidnet_b200 import synth
-    import oracle  # noqa: F401  (only for the plume-BC builder shared with the tests)
+    import torch
+    from fluidnet_b200 import synth, simulate
     flags = synth.make_flags(n, n, n, True, nb=1, geometry=True)
     U = synth.make_smooth_velocity(flags, True, amp=2.0)
     density = synth.make_density(flags)
     batch = {"pDiv": np.zeros_like(flags), "UDiv": U, "flags": flags, "density": density}
-    from oracle.api import create_plume_bcs
-    create_plume_bcs(batch, [1.0], n / 128.0, 0.15)
+    # Plume inflow BCs from the product's own host mirror of tfluids.createPlumeBCs (lib/simulate.lua:47-123);
+    # nothing under oracle/ is touched on this arm's input path.
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    simulate.createPlumeBCs(tb, [1.0], n / 128.0, 0.15)
+    for k in ("UBC", "UBCInvMask", "densityBC", "densityBCInvMask"):
+        batch[k] = tb[k].numpy()
     # fluid_net_3d_sim.lua:73-87
     mconf = dict(dt=0.1, advectionMethod="maccormackOurs", maccormackStrength=0.6,
                  buoyancyScale=2.0 * n / 128.0, gravityScale=0.0, gravity=None,
