@@ -59,3 +59,38 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle", txt, flags=re.M), f
                 assert "liboracle" not in txt and "libtfluids_ref" not in txt, f
+
+
+def test_lua_shim_is_consistent_with_the_header():
+    """fluidnet_b200/lua/tfluids_ffi.lua cannot be executed here (no LuaJIT), so it is checked statically:
+    every function its ffi.cdef declares exists in include/tfl.h with the same number of parameters, every
+    lib.tfl_* it calls is declared, and it defines every tfluids.* function of the reference's init.lua that
+    the library implements."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def decls(text):
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        out = {}
+        for m in re.finditer(r"\b(tfl_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+            args = m.group(2).strip()
+            out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+        return out
+
+    header = decls(open(os.path.join(root, "include", "tfl.h")).read())
+    lua = open(os.path.join(root, "fluidnet_b200", "lua", "tfluids_ffi.lua")).read()
+    start = lua.index("ffi.cdef[[")
+    cdef = decls(lua[start:lua.index("]]", start)])
+    assert len(cdef) >= 30
+    assert not set(cdef) - set(header), sorted(set(cdef) - set(header))
+    assert not [(k, header[k], cdef[k]) for k in cdef if header[k] != cdef[k]]
+    assert not set(re.findall(r"lib\.(tfl_[a-z0-9_]+)", lua)) - set(cdef)
+    defined = set(re.findall(r"^function tfluids\.([A-Za-z]+)", lua, flags=re.M))
+    for name in ("advectScalar", "advectVel", "setWallBcsForward", "velocityDivergenceForward", "velocityUpdateForward",
+                 "addBuoyancy", "addGravity", "vorticityConfinement", "solveLinearSystemJacobi", "solveLinearSystemPCG",
+                 "emptyDomain", "flagsToOccupancy", "normalizePressureMean", "rectangularBlur", "signedDistanceField",
+                 "volumetricUpSamplingNearestForward", "volumetricUpSamplingNearestBackward",
+                 "velocityDivergenceBackward", "velocityUpdateBackward"):
+        assert name in defined, name
