@@ -18,7 +18,13 @@
  * Jacobi has no CPU reference (generic/tfluids.cc:836-839 errors out); it is restated
  * from the CUDA kernel + host loop generic/tfluids.cu:1765-1927.  The conv stack lives
  * in un-vendored cuDNN/cudnn.torch (README.md:35-52): textbook cross-correlation here,
- * "parity unpinned" for that part.
+ * "parity unpinned" for that part (the model-graph semantics around it are pinned on
+ * torch.nn.functional, tests/test_oracle_model_graph.py).  The PCG solver is CUDA-only in the
+ * reference too (generic/tfluids.cu:1245-1759): its algorithm is restated, its connected-component
+ * labelling is pinned on the reference's CPU code, its iterates are "parity unpinned" and checked by the
+ * reference test's own criteria.  The operators around the step (blur, signed distance, up-sampling,
+ * pressure-mean removal) and the three backward operators are pinned on the compiled reference like the
+ * step operators (tests/test_oracle_aux_ops.py, tests/test_oracle_edge_sizes.py).
  *
  * Layout everywhere: 5-D [b][c][z][y][x], x fastest, float32.
  * All file:line citations are relative to /root/reference/torch/.
