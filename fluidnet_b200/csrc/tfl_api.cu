@@ -43,6 +43,15 @@ struct tfl_ctx {
     bool density_sent = false;
   } ov;
   PcgScratch pcg;                           // grow-only buffers of the PCG solve
+  // Byte copy of the step's flags and their clearance field (advection fast path), kept between steps:
+  // each step re-derives the bytes, compares them with the copy on the device and rebuilds the
+  // clearance only if something changed (no host round trip).
+  struct {
+    unsigned char* bytes = nullptr;         // [3][cells]: flags, clearance, scratch
+    size_t cells = 0;
+    int nb = 0, nz = 0, ny = 0, nx = 0;
+    int* changed = nullptr;                 // device word
+  } fcache;
 };
 
 struct tfl_cnn {
@@ -175,6 +184,44 @@ void widen_for_forward_pass(const tfl_ctx* ctx, const Geo& g, Geo* gf) {
   gf->zhi = std::min(hi_lim, g.zhi + ctx->slab_margin);
 }
 
+// (Re)allocates the flag-byte cache for this grid shape; a new cache starts "changed" (the word stays set
+// until a step has rebuilt the clearance: the step resets it after the rebuild is enqueued).
+int flag_cache_ensure(tfl_ctx* ctx, const Geo& g) {
+  auto& fc = ctx->fcache;
+  const size_t cells = (size_t)g.n * g.nb;
+  if (!fc.changed) {
+    void* p = nullptr;
+    TFL_CUDA(ctx, cudaMalloc(&p, sizeof(int)));
+    fc.changed = (int*)p;
+  }
+  if (fc.bytes && fc.cells == cells && fc.nb == g.nb && fc.nz == g.nz && fc.ny == g.ny && fc.nx == g.nx) {
+    TFL_CUDA(ctx, cudaMemsetAsync(fc.changed, 0, sizeof(int), ctx->stream));
+    return 0;
+  }
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (fc.bytes) cudaFree(fc.bytes);
+  fc.bytes = nullptr;
+  void* p = nullptr;
+  TFL_CUDA(ctx, cudaMalloc(&p, 3 * cells + 64));
+  fc.bytes = (unsigned char*)p;
+  fc.cells = cells; fc.nb = g.nb; fc.nz = g.nz; fc.ny = g.ny; fc.nx = g.nx;
+  TFL_CUDA(ctx, cudaMemsetAsync(fc.bytes, 0, 3 * cells + 64, ctx->stream));
+  TFL_CUDA(ctx, cudaMemsetAsync(fc.changed, 1, sizeof(int), ctx->stream));     // non-zero: rebuild
+  return 0;
+}
+
+// Byte flags + clearance field of `flags` for this call, through the context's cache: the bytes are
+// re-derived and compared on the device, the clearance is rebuilt only when one differs.
+int prepare_flags(tfl_ctx* ctx, const float* flags, const Geo& g, unsigned char** fl8, unsigned char** clear) {
+  if (flag_cache_ensure(ctx, g)) return 1;
+  const size_t cells = (size_t)g.n * g.nb;
+  *fl8 = ctx->fcache.bytes;
+  *clear = ctx->fcache.bytes + cells;
+  launch_flags_to_u8(flags, *fl8, (long long)cells, ctx->fcache.changed, ctx->stream);
+  ctx->launches += 1 + launch_clearance(*fl8, *clear, *clear + cells, g, ctx->fcache.changed, ctx->stream);
+  return 0;
+}
+
 float get_dx(const Geo& g) {     // third_party/grid.cc:37-40 on the GLOBAL grid
   int m = g.nx > g.ny ? g.nx : g.ny;
   if (g.gnz > m) m = g.gnz;
@@ -232,6 +279,8 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->dscratch) cudaFree(ctx->dscratch);
   pcg_release(ctx->pcg);
+  if (ctx->fcache.bytes) cudaFree(ctx->fcache.bytes);
+  if (ctx->fcache.changed) cudaFree(ctx->fcache.changed);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -437,11 +486,14 @@ int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid*
   float* fwd = cv.take<float>(cells);
   float* fwd_pos = cv.take<float>(cells * g.nc);
   float* tmp = cv.take<float>(cells);
+  unsigned char *fl8 = nullptr, *clear = nullptr;
   float* dst = in_place ? tmp : s_dst->data;
   Geo gf = g;     // forward pass on a wider range: its halo planes feed the backward pass
   widen_for_forward_pass(ctx, g, &gf);
-  const int nl = launch_advect_scalar(dt, s->data, U->data, flags->data, method, sample_outside_fluid,
-                                      strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
+  const bool traced = method == TFL_ADVECT_EULER_OURS || method == TFL_ADVECT_MACCORMACK_OURS;
+  if (traced && prepare_flags(ctx, flags->data, g, &fl8, &clear)) return 1;
+  const int nl = launch_advect_scalar(dt, s->data, U->data, flags->data, traced ? clear : nullptr, method,
+                                      sample_outside_fluid, strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectScalar: bad method");
   ctx->launches += nl;
   if (check_launch(ctx, "advectScalar")) return 1;
@@ -469,10 +521,14 @@ int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* fl
   Carver cv(ctx);
   float* fwd = cv.take<float>(cells * g.nc);
   float* tmp = cv.take<float>(cells * g.nc);
+  unsigned char *fl8 = nullptr, *clear = nullptr;
   float* dst = in_place ? tmp : U_dst->data;
   Geo gf = g;
   widen_for_forward_pass(ctx, g, &gf);
-  const int nl = launch_advect_vel(dt, U->data, flags->data, method, strength, dst, fwd, g, gf, ctx->stream);
+  const bool traced = method != TFL_ADVECT_EULER && method != TFL_ADVECT_MACCORMACK;
+  if (traced && prepare_flags(ctx, flags->data, g, &fl8, &clear)) return 1;
+  const int nl = launch_advect_vel(dt, U->data, flags->data, traced ? clear : nullptr, method, strength, dst, fwd, g,
+                                   gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectVel: bad method");
   ctx->launches += nl;
   if (check_launch(ctx, "advectVel")) return 1;
@@ -1052,7 +1108,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   const bool has_density = s->density.data != nullptr;
   if (cnn_ensure_act(ctx, m, g)) return 1;
   if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4, cells * 4 * g.nc, cells * 4 * g.nc,
-                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells, cells * 12})))
+                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells * 12})))
     return 1;
   Carver cv(ctx);
   float* fwd_s = cv.take<float>(cells);
@@ -1064,12 +1120,12 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   float* cnorm = cv.take<float>(cells);
   float* p_net = cv.take<float>(cells);
   float* scale = cv.take<float>(g.nb);
-  unsigned char* fl8 = cv.take<unsigned char>(cells);
   float* force = cv.take<float>(cells * 3);
   cudaStream_t st = ctx->stream;
-  // Byte copy of the flags for this step (every bit the kernels test is below 256).
-  launch_flags_to_u8(s->flags.data, fl8, (long long)cells, st);
-  ctx->launches += 1;
+  // Byte copy of the flags for this step (every bit the kernels test is below 256) and, when a byte
+  // differs from the previous step's copy, the clearance field of the advection fast path.
+  unsigned char *fl8 = nullptr, *clear = nullptr;
+  if (prepare_flags(ctx, s->flags.data, g, &fl8, &clear)) return 1;
   const bool ov = ctx->ov.active;
   if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_u_in, 0));          // U has arrived from the host
   if (has_density) {
@@ -1078,14 +1134,14 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
     if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_d_in, 0));
-    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, mc->advection_method, 0,
+    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, clear, mc->advection_method, 0,
                                         mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
     if (nl < 0) return fail(ctx, "advectScalar: bad method");
     ctx->launches += nl;
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
   }
   {
-    const int nl = launch_advect_vel(mc->dt, s->U.data, fl8, mc->advection_method,
+    const int nl = launch_advect_vel(mc->dt, s->U.data, fl8, clear, mc->advection_method,
                                      mc->maccormack_strength, tmp_u, fwd_u, g, g, st);
     if (nl < 0) return fail(ctx, "advectVel: bad method");
     ctx->launches += nl;

@@ -354,6 +354,45 @@ __device__ inline bool line_trace(const FT* __restrict__ fl, const Geo& g, V3 po
 }
 
 // ---------------------------------------------------------------------------------------
+// Clear-space fast path.  clear[c] = largest r <= kClearMax such that every cell within
+// Chebyshev distance r of c lies inside the local storage and is fluid (0: no guarantee; 2-D
+// grids ignore z).  A trace of length < r that starts at the centre of c never meets a
+// non-fluid cell or the domain border, its interpolation footprint needs no index clamp and
+// no slab-range test: the code below is line_trace / build_index / lerp_at with the branches
+// that cannot fire removed -- the arithmetic, and its order, are unchanged (bit-identical).
+// ---------------------------------------------------------------------------------------
+constexpr int kClearMax = 7;
+#define TFL_CLEAR_SLACK 0.01f      // covers |dir| <= 1 + ulps and the accumulated step rounding
+
+__device__ __forceinline__ V3 line_trace_clear(V3 pos, V3 delta, float length) {
+  V3 out = pos;
+  if (length <= TFL_TRACE_EPS) return out;
+  const V3 dir = {delta.x / length, delta.y / length, delta.z / length};
+  float travelled = 0.0f;
+  while (travelled < (length - TFL_HIT_MARGIN)) {
+    const float step = std_min(length - travelled, 1.0f);
+    out = V3{out.x + dir.x * step, out.y + dir.y * step, out.z + dir.z * step};
+    travelled += step;
+  }
+  return out;
+}
+// build_index + corner without the clamps (positions at least one cell away from every end of the
+// local storage, guaranteed by the clearance test).
+__device__ __forceinline__ int build_index_clear(const Geo& g, V3 pos, Lerp& q) {
+  const float px = pos.x - 0.5f, py = pos.y - 0.5f, pz = pos.z - 0.5f;
+  q.xi = (int)px; q.yi = (int)py; q.zi = (int)pz;
+  q.s1 = px - (float)q.xi; q.s0 = 1.0f - q.s1;
+  q.t1 = py - (float)q.yi; q.t0 = 1.0f - q.t1;
+  q.f1 = pz - (float)q.zi; q.f0 = 1.0f - q.f1;
+  return cell(g, g.is3d ? q.zi - g.zoff : 0, q.yi, q.xi);
+}
+__device__ __forceinline__ float lerp_block_clear(const float* __restrict__ blk, const Geo& g, V3 pos) {
+  Lerp q;
+  const int o = build_index_clear(g, pos, q);
+  return lerp_at(blk, g, q, o);
+}
+
+// ---------------------------------------------------------------------------------------
 // Launch geometry shared by the per-cell kernels.
 // ---------------------------------------------------------------------------------------
 // (b, k, j, i) of this thread; returns false if outside the launch range.

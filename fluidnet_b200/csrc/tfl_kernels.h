@@ -26,19 +26,26 @@ template <typename FT>
 int launch_vorticity(float* U, const FT* flags, float strength, float* curl, float* cnorm, float* force,
                      const Geo& g, cudaStream_t st);
 // g: range of the result; g_fwd: (wider, in slab mode) range of the forward pass.
+// clear: clearance field of the same grid (launch_clearance) or nullptr (general code everywhere).
 template <typename FT>
-int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, int method,
-                         int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
-                         const Geo& g_fwd, cudaStream_t st);
+int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, const unsigned char* clear,
+                         int method, int outside, float strength, float* dst, float* fwd, float* fwd_pos,
+                         const Geo& g, const Geo& g_fwd, cudaStream_t st);
 template <typename FT>
-int launch_advect_vel(float dt, const float* U, const FT* flags, int method, float strength, float* dst,
-                      float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st);
+int launch_advect_vel(float dt, const float* U, const FT* flags, const unsigned char* clear, int method,
+                      float strength, float* dst, float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st);
+// Clearance of every cell of the local storage (advection fast path, tfl_device.cuh); tmp: scratch of the
+// same size; gate: optional device word, the kernels do nothing when it is 0.  Returns the launch count.
+template <typename FT>
+int launch_clearance(const FT* flags, unsigned char* clear, unsigned char* tmp, const Geo& g, const int* gate,
+                     cudaStream_t st);
 template <typename FT>
 void launch_jacobi_mask(const FT* flags, unsigned char* mask, const Geo& g, cudaStream_t st);
 void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
                         const Geo& g, cudaStream_t st);
 void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st);
-void launch_flags_to_u8(const float* f, unsigned char* o, long long n, cudaStream_t st);
+// changed: optional device word that is OR-ed with 1 when a byte differs from what `o` held before.
+void launch_flags_to_u8(const float* f, unsigned char* o, long long n, int* changed, cudaStream_t st);
 void launch_apply_bc(float* x, const float* inv, const float* bc, long long n, cudaStream_t st);
 void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st);
 

@@ -298,17 +298,45 @@ __device__ __forceinline__ float advect_scalar_cell(const FT* __restrict__ fl, c
   return sample_scalar(src, fl, g, back, outside);
 }
 
+// eulerOurs / maccormackOurs pass for a cell with clearance (fluid, interior): trace + sample with the
+// branches that cannot fire removed; every corner of the footprint is fluid, so interpolWithFluid is the
+// plain trilinear expression (same products, same order).
+template <typename FT>
+__device__ __forceinline__ float advect_scalar_cell_clear(const FT* __restrict__ fl, const float* __restrict__ ub,
+                                                          const float* __restrict__ src, const Geo& g, float dt,
+                                                          int k, int j, int i, bool outside, float reach,
+                                                          V3* pos_out) {
+  const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
+  const V3 delta = scale3(mac_centered(ub, g, k, j, i), -dt);
+  const float length = norm3(delta);
+  if (length < reach) {
+    const V3 back = line_trace_clear(start, delta, length);
+    if (pos_out) *pos_out = back;
+    return lerp_block_clear(src, g, back);
+  }
+  V3 back;
+  line_trace(fl, g, start, delta, &back);
+  if (pos_out) *pos_out = back;
+  return sample_scalar(src, fl, g, back, outside);
+}
+
 template <bool IS3D, typename FT, int METHOD>
 __global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* __restrict__ U,
-                                      const FT* __restrict__ flags, float* __restrict__ out,
-                                      float* __restrict__ pos_out, float dt, int outside, Geo gin) {
+                                      const FT* __restrict__ flags, const unsigned char* __restrict__ clear,
+                                      float* __restrict__ out, float* __restrict__ pos_out, float dt,
+                                      int outside, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const int c = cell(g, k, j, i);
   float v = 0.0f;
   V3 pos = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
-  if (!on_border(g, k, j, i)) {
+  constexpr bool kTraced = METHOD == TFL_ADVECT_EULER_OURS || METHOD == TFL_ADVECT_MACCORMACK_OURS;
+  const int clr = (kTraced && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
+  if (clr > 0) {
+    v = advect_scalar_cell_clear(flags + b * g.n, U + (long long)b * g.nc * g.n, s + b * g.n, g, dt, k, j, i,
+                                 outside != 0, (float)clr - TFL_CLEAR_SLACK, pos_out ? &pos : nullptr);
+  } else if (!on_border(g, k, j, i)) {
     v = advect_scalar_cell<METHOD>(flags + b * g.n, U + (long long)b * g.nc * g.n, s + b * g.n, g, dt, k,
                                    j, i, outside != 0, pos_out ? &pos : nullptr);
   }
@@ -326,23 +354,28 @@ __global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* 
 template <bool IS3D, typename FT>
 __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const float* __restrict__ fwd,
                                            const float* __restrict__ fwd_pos, const float* __restrict__ U,
-                                           const FT* __restrict__ flags, float* __restrict__ dst,
-                                           float dt, float strength, int outside, Geo gin) {
+                                           const FT* __restrict__ flags, const unsigned char* __restrict__ clear,
+                                           float* __restrict__ dst, float dt, float strength, int outside, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const int c = cell(g, k, j, i);
   const FT* fl = flags + b * g.n;
+  const unsigned char* cl = clear ? clear + b * g.n : nullptr;
   const float* sb = s + b * g.n;
   const float* fb = fwd + b * g.n;
   const float fw = __ldg(fb + c);
-  const bool border = on_border(g, k, j, i);
+  const int clr = cl ? (int)__ldg(cl + c) : 0;
+  const bool border = clr > 0 ? false : on_border(g, k, j, i);
   float bw = 0.0f;
-  if (!border)
+  if (clr > 0)
+    bw = advect_scalar_cell_clear(fl, U + (long long)b * g.nc * g.n, fb, g, -dt, k, j, i, outside != 0,
+                                  (float)clr - TFL_CLEAR_SLACK, nullptr);
+  else if (!border)
     bw = advect_scalar_cell<TFL_ADVECT_MACCORMACK_OURS>(fl, U + (long long)b * g.nc * g.n, fb, g, -dt, k,
                                                         j, i, outside != 0, nullptr);
   float v = fw;
-  if (flag_i(fl, g, k, j, i) & kFluid) {
+  if (clr > 0 || (flag_i(fl, g, k, j, i) & kFluid)) {
     const float diff = __ldg(sb + c) - bw;
     v = (float)((double)v + ((double)strength * 0.5) * (double)diff);
   }
@@ -361,6 +394,25 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
       // 27 (9 in 2-D) neighbours sit at fixed offsets from the centre.
       const int ctr = cell(g, g.is3d ? kl0 : 0, j0, i0);
       const int sy = g.nx, sz = g.nx * g.ny;
+      // clearance >= 1 at the centre of the neighbourhood: all of it is fluid, no flag is read
+      const bool all_fluid = outside || (cl && __ldg(cl + ctr) > 0);
+      if (all_fluid) {
+        found = 1;
+#pragma unroll
+        for (int dz = -1; dz <= 1; dz++) {
+          if (!g.is3d && dz != 0) continue;
+#pragma unroll
+          for (int dy = -1; dy <= 1; dy++) {
+            const float* srow = sb + (ctr + dz * sz + dy * sy);
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+              const float t = __ldg(srow + dx);
+              lo = (t < lo) ? t : lo;
+              hi = (t > hi) ? t : hi;
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int dz = -1; dz <= 1; dz++) {
         if (!g.is3d && dz != 0) continue;
@@ -372,12 +424,13 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
 #pragma unroll
           for (int dx = -1; dx <= 1; dx++) {
             const float t = __ldg(srow + dx);
-            const bool use = outside || (flag_at(frow, dx) & kFluid);
+            const bool use = (flag_at(frow, dx) & kFluid);
             lo = (use && t < lo) ? t : lo;
             hi = (use && t > hi) ? t : hi;
             found |= use ? 1 : 0;
           }
         }
+      }
       }
     } else {
     for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
@@ -507,6 +560,30 @@ __device__ __forceinline__ V3 advect_mac_cell(const FT* __restrict__ fl, const V
   }
   return r;
 }
+// The "Ours" back-trace of one face component in clear space (see tfl_device.cuh): `reach` is the
+// cell's clearance minus the slack; a longer trace takes the general code.
+template <typename FT>
+__device__ __forceinline__ float advect_mac_component_clear(const FT* __restrict__ fl, V3 vel,
+                                                            const float* __restrict__ src_c, const Geo& g,
+                                                            float dt, V3 start, float reach) {
+  const V3 delta = scale3(vel, -dt);
+  const float length = norm3(delta);
+  if (length < reach) return lerp_block_clear(src_c, g, line_trace_clear(start, delta, length));
+  V3 p;
+  line_trace(fl, g, start, delta, &p);
+  return lerp_block(src_c, g, p);
+}
+template <typename FT>
+__device__ __forceinline__ V3 advect_mac_cell_clear(const FT* __restrict__ fl, const V3 (&vel)[3],
+                                                    const float* __restrict__ src, const Geo& g, float dt,
+                                                    int k, int j, int i, float reach) {
+  const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
+  V3 r;
+  r.x = advect_mac_component_clear(fl, vel[0], src, g, dt, start, reach);
+  r.y = advect_mac_component_clear(fl, vel[1], src + g.n, g, dt, start, reach);
+  r.z = g.is3d ? advect_mac_component_clear(fl, vel[2], src + 2 * g.n, g, dt, start, reach) : 0.0f;
+  return r;
+}
 __device__ __forceinline__ void mac_face_velocities(const float* __restrict__ ub, const Geo& g, int k, int j, int i,
                                                     V3 (&vel)[3]) {
   vel[0] = mac_at_x(ub, g, k, j, i);
@@ -524,14 +601,19 @@ __device__ __forceinline__ void mac_face_velocities(const float* __restrict__ ub
 
 template <bool IS3D, typename FT, bool OURS>
 __global__ void __launch_bounds__(256, TFL_ADVECT_MINB1) k_advect_vel_pass1(const float* __restrict__ U, const FT* __restrict__ flags,
-                                   float* __restrict__ out, float dt, Geo gin) {
+                                   const unsigned char* __restrict__ clear, float* __restrict__ out, float dt, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
   const int c = cell(g, k, j, i);
   const float* ub = U + (long long)b * g.nc * g.n;
   V3 v = {0.0f, 0.0f, 0.0f};
-  if (!on_border(g, k, j, i)) {
+  const int clr = (OURS && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
+  if (clr > 0) {                            // fluid, interior, clear neighbourhood
+    V3 vel[3];
+    mac_face_velocities(ub, g, k, j, i, vel);
+    v = advect_mac_cell_clear(flags + b * g.n, vel, ub, g, dt, k, j, i, (float)clr - TFL_CLEAR_SLACK);
+  } else if (!on_border(g, k, j, i)) {
     V3 vel[3];
     mac_face_velocities(ub, g, k, j, i, vel);
     v = advect_mac_cell<OURS>(flags + b * g.n, vel, ub, g, dt, k, j, i);
@@ -571,12 +653,38 @@ __device__ __forceinline__ float clamp_component_mac(const float* __restrict__ o
   return clamp_f(val, lo, hi);
 }
 
+// The same clamp where the cell's clearance exceeds |vel|: both 2x2x2 boxes lie inside the local
+// storage, so the index clamps and the bounds test cannot fire.
+__device__ __forceinline__ float clamp_component_mac_clear(const float* __restrict__ orig_c, const Geo& g,
+                                                           float val, int kloc, int j, int i, V3 vel) {
+  const float fi = (float)i, fj = (float)j, fk = (float)(kloc + g.zoff);
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  const int sy = g.nx, sz = g.nx * g.ny;
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    const int i0 = l == 0 ? (int)(fi - vel.x) : (int)(fi + vel.x);
+    const int j0 = l == 0 ? (int)(fj - vel.y) : (int)(fj + vel.y);
+    const int k0 = g.is3d ? (l == 0 ? (int)(fk - vel.z) : (int)(fk + vel.z)) - g.zoff : 0;
+    const float* a0 = orig_c + cell(g, k0, j0, i0);
+    const float* a1 = a0 + sy;
+#define TFL_MM(ptr, off) { const float t = __ldg((ptr) + (off)); if (t < lo) lo = t; if (t > hi) hi = t; }
+    TFL_MM(a0, 0) TFL_MM(a0, 1) TFL_MM(a1, 0) TFL_MM(a1, 1)
+    if (g.is3d) {
+      const float* b0 = a0 + sz;
+      const float* b1 = b0 + sy;
+      TFL_MM(b0, 0) TFL_MM(b0, 1) TFL_MM(b1, 0) TFL_MM(b1, 1)
+    }
+#undef TFL_MM
+  }
+  return clamp_f(val, lo, hi);
+}
+
 // Backward pass on the forward field + MacCormackCorrectMAC + MacCormackClampMAC, fused
 // (third_party/tfluids.cc:859-915, 660-774).
 template <bool IS3D, typename FT, bool OURS>
 __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(const float* __restrict__ U, const float* __restrict__ fwd,
-                                   const FT* __restrict__ flags, float* __restrict__ dst, float dt,
-                                   float strength, Geo gin) {
+                                   const FT* __restrict__ flags, const unsigned char* __restrict__ clear,
+                                   float* __restrict__ dst, float dt, float strength, Geo gin) {
   const Geo g = static_geo<IS3D>(gin);
   int b, k, j, i;
   if (!thread_cell(g, b, k, j, i)) return;
@@ -584,6 +692,30 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(cons
   const FT* fl = flags + b * g.n;
   const float* ub = U + (long long)b * g.nc * g.n;
   const float* fb = fwd + (long long)b * g.nc * g.n;
+  float* db = dst + (long long)b * g.nc * g.n + c;
+  const int clr = (OURS && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
+  if (clr > 0) {
+    // Fluid cell whose 26 neighbours are fluid: interior, no face is skipped by the correction.
+    const float reach = (float)clr - TFL_CLEAR_SLACK;
+    V3 vel[3];
+    mac_face_velocities(ub, g, k, j, i, vel);
+    const V3 bw = advect_mac_cell_clear(fl, vel, fb, g, -dt, k, j, i, reach);
+    const float bwv[3] = {bw.x, bw.y, bw.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (a < g.nc) {
+        const float fw = __ldg(fb + a * g.n + c);
+        const float diff = __ldg(ub + a * g.n + c) - bwv[a];
+        float v = (float)((double)fw + ((double)strength * 0.5) * (double)diff);
+        const V3 d = scale3(vel[a], dt);
+        // |d| is the trace length of this component (the trace displacement is -d)
+        if (norm3(d) < reach) v = clamp_component_mac_clear(ub + a * g.n, g, v, k, j, i, d);
+        else v = clamp_component_mac(ub + a * g.n, g, v, fw, k + g.zoff, j, i, d);
+        db[a * g.n] = v;
+      }
+    }
+    return;
+  }
   const bool border = on_border(g, k, j, i);
   V3 bw = {0.0f, 0.0f, 0.0f};
   V3 vel[3];
@@ -615,7 +747,6 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(cons
       val[2] = clamp_component_mac(ub + 2 * g.n, g, val[2], fwv[2], kg, j, i,
                                    scale3(vel[2], dt));
   }
-  float* db = dst + (long long)b * g.nc * g.n + c;
   for (int a = 0; a < g.nc; a++) db[a * g.n] = val[a];
 }
 
@@ -920,52 +1051,52 @@ int launch_vorticity(float* U, const FT* flags, float strength, float* curl, flo
 }
 
 template <typename FT>
-int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, int method,
-                         int outside, float strength, float* dst, float* fwd, float* fwd_pos, const Geo& g,
-                         const Geo& g_fwd, cudaStream_t st) {
+int launch_advect_scalar(float dt, const float* s, const float* U, const FT* flags, const unsigned char* clear,
+                         int method, int outside, float strength, float* dst, float* fwd, float* fwd_pos,
+                         const Geo& g, const Geo& g_fwd, cudaStream_t st) {
   switch (method) {
     case TFL_ADVECT_EULER:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER, g, st, s, U, flags, clear, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_EULER_OURS:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_EULER_OURS, g, st, s, U, flags, clear, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_RK2_OURS:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK2_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK2_OURS, g, st, s, U, flags, clear, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_RK3_OURS:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK3_OURS, g, st, s, U, flags, dst, nullptr, dt, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_RK3_OURS, g, st, s, U, flags, clear, dst, nullptr, dt, outside, g);
       return 1;
     case TFL_ADVECT_MACCORMACK:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK, g_fwd, st, s, U, flags, fwd, nullptr, dt, outside, g_fwd);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK, g_fwd, st, s, U, flags, clear, fwd, nullptr, dt, outside, g_fwd);
       TFL_LAUNCH3(k_advect_scalar_pass2_manta, FT, g, st, s, fwd, U, flags, dst, dt, strength, g);
       return 2;
     case TFL_ADVECT_MACCORMACK_OURS:
-      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK_OURS, g_fwd, st, s, U, flags, fwd, fwd_pos, dt, outside, g_fwd);
-      TFL_LAUNCH3(k_advect_scalar_pass2_ours, FT, g, st, s, fwd, fwd_pos, U, flags, dst, dt, strength, outside, g);
+      TFL_LAUNCH3X(k_advect_scalar_pass1, FT, TFL_ADVECT_MACCORMACK_OURS, g_fwd, st, s, U, flags, clear, fwd, fwd_pos, dt, outside, g_fwd);
+      TFL_LAUNCH3(k_advect_scalar_pass2_ours, FT, g, st, s, fwd, fwd_pos, U, flags, clear, dst, dt, strength, outside, g);
       return 2;
   }
   return -1;
 }
 
 template <typename FT>
-int launch_advect_vel(float dt, const float* U, const FT* flags, int method, float strength, float* dst,
-                      float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st) {
+int launch_advect_vel(float dt, const float* U, const FT* flags, const unsigned char* clear, int method,
+                      float strength, float* dst, float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st) {
   if (method == TFL_ADVECT_RK2_OURS || method == TFL_ADVECT_RK3_OURS) method = TFL_ADVECT_MACCORMACK_OURS;
   switch (method) {
     case TFL_ADVECT_EULER:
-      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g, st, U, flags, dst, dt, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g, st, U, flags, clear, dst, dt, g);
       return 1;
     case TFL_ADVECT_EULER_OURS:
-      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g, st, U, flags, dst, dt, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g, st, U, flags, clear, dst, dt, g);
       return 1;
     case TFL_ADVECT_MACCORMACK:
-      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g_fwd, st, U, flags, fwd, dt, g_fwd);
-      TFL_LAUNCH3X(k_advect_vel_pass2, FT, false, g, st, U, fwd, flags, dst, dt, strength, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, false, g_fwd, st, U, flags, clear, fwd, dt, g_fwd);
+      TFL_LAUNCH3X(k_advect_vel_pass2, FT, false, g, st, U, fwd, flags, clear, dst, dt, strength, g);
       return 2;
     case TFL_ADVECT_MACCORMACK_OURS:
-      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g_fwd, st, U, flags, fwd, dt, g_fwd);
-      TFL_LAUNCH3X(k_advect_vel_pass2, FT, true, g, st, U, fwd, flags, dst, dt, strength, g);
+      TFL_LAUNCH3X(k_advect_vel_pass1, FT, true, g_fwd, st, U, flags, clear, fwd, dt, g_fwd);
+      TFL_LAUNCH3X(k_advect_vel_pass2, FT, true, g, st, U, fwd, flags, clear, dst, dt, strength, g);
       return 2;
   }
   return -1;
@@ -1028,22 +1159,102 @@ void launch_clamp(float* x, float lo, float hi, long long n, cudaStream_t st) {
   template void launch_add_buoyancy<FT>(float*, const FT*, const float*, const float*, const Geo&, cudaStream_t); \
   template void launch_add_gravity<FT>(float*, const FT*, const float*, const Geo&, cudaStream_t);           \
   template int launch_vorticity<FT>(float*, const FT*, float, float*, float*, float*, const Geo&, cudaStream_t); \
-  template int launch_advect_scalar<FT>(float, const float*, const float*, const FT*, int, int, float, float*, \
-                                        float*, float*, const Geo&, const Geo&, cudaStream_t);               \
-  template int launch_advect_vel<FT>(float, const float*, const FT*, int, float, float*, float*, const Geo&,  \
-                                     const Geo&, cudaStream_t);                                              \
+  template int launch_advect_scalar<FT>(float, const float*, const float*, const FT*, const unsigned char*, int, int, \
+                                        float, float*, float*, float*, const Geo&, const Geo&, cudaStream_t);  \
+  template int launch_advect_vel<FT>(float, const float*, const FT*, const unsigned char*, int, float, float*, \
+                                     float*, const Geo&, const Geo&, cudaStream_t);                          \
   template void launch_jacobi_mask<FT>(const FT*, unsigned char*, const Geo&, cudaStream_t);
 TFL_INSTANTIATE(float)
 TFL_INSTANTIATE(unsigned char)
 #undef TFL_INSTANTIATE
 
-// float flags -> byte flags (once per fused step).
-__global__ void k_flags_to_u8(const float* __restrict__ f, unsigned char* __restrict__ o, long long n) {
+// ---------------------------------------------------------------------------------------
+// Clearance field of the advection fast path (tfl_device.cuh): three separable passes over the LOCAL
+// storage.  x: run of fluid cells around the cell; y, z: largest r such that the previous pass' value
+// is >= r on every line cell within r.
+// ---------------------------------------------------------------------------------------
+template <typename FT>
+__global__ void k_clear_x(const FT* __restrict__ flags, unsigned char* __restrict__ out, Geo g,
+                          const int* __restrict__ gate) {
+  int b, k, j, i;
+  if (gate && *gate == 0) return;          // flags unchanged since the cached field was built
+  if (!thread_cell(g, b, k, j, i)) return;
+  const FT* row = flags + b * g.n + cell(g, k, j, 0);
+  int r = -1;
+  if (flag_at(row, i) & kFluid) {
+    r = 0;
+    for (int d = 1; d <= kClearMax; d++) {
+      if (i - d < 0 || i + d >= g.nx || !(flag_at(row, i - d) & kFluid) || !(flag_at(row, i + d) & kFluid)) break;
+      r = d;
+    }
+  }
+  // 255 marks a non-fluid cell for the next pass (clearance 0 is "fluid, no clear neighbourhood")
+  out[b * g.n + cell(g, k, j, i)] = (unsigned char)(r < 0 ? 255 : r);
+}
+// AXIS 1: y, 2: z.  `in` holds the previous pass (255 = non-fluid), `out` the combined radius; the last
+// pass writes 0 for non-fluid cells.
+template <int AXIS, bool LAST>
+__global__ void k_clear_axis(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, Geo g,
+                             const int* __restrict__ gate) {
+  int b, k, j, i;
+  if (gate && *gate == 0) return;
+  if (!thread_cell(g, b, k, j, i)) return;
+  const int c = b * g.n + cell(g, k, j, i);
+  const int stride = AXIS == 1 ? g.nx : g.nx * g.ny;
+  const int pos = AXIS == 1 ? j : k, ext = AXIS == 1 ? g.ny : g.nz;
+  const int self = in[c];
+  int r;
+  if (self == 255) {
+    r = LAST ? 0 : 255;
+  } else {
+    r = 0;
+    int m = self;
+    for (int d = 1; d <= kClearMax; d++) {
+      if (pos - d < 0 || pos + d >= ext) break;
+      const int a = in[c - d * stride], bb = in[c + d * stride];
+      if (a == 255 || bb == 255) break;
+      m = min(m, min(a, bb));
+      if (m < d) break;
+      r = d;
+    }
+  }
+  out[c] = (unsigned char)r;
+}
+template <typename FT>
+int launch_clearance(const FT* flags, unsigned char* clear, unsigned char* tmp, const Geo& gin, const int* gate,
+                     cudaStream_t st) {
+  Geo g = gin;
+  g.zlo = 0; g.zhi = g.nz;                 // the whole local storage, whatever range the operator computes
+  dim3 grid, block;
+  launch_dims(g, grid, block);
+  if (g.is3d) {                            // (a 3-D grid with fewer than 3 planes gets clearance 0)
+    k_clear_x<FT><<<grid, block, 0, st>>>(flags, clear, g, gate);
+    k_clear_axis<1, false><<<grid, block, 0, st>>>(clear, tmp, g, gate);
+    k_clear_axis<2, true><<<grid, block, 0, st>>>(tmp, clear, g, gate);
+    return 3;
+  }
+  k_clear_x<FT><<<grid, block, 0, st>>>(flags, tmp, g, gate);
+  k_clear_axis<1, true><<<grid, block, 0, st>>>(tmp, clear, g, gate);
+  return 2;
+}
+template int launch_clearance<float>(const float*, unsigned char*, unsigned char*, const Geo&, const int*, cudaStream_t);
+template int launch_clearance<unsigned char>(const unsigned char*, unsigned char*, unsigned char*, const Geo&, const int*,
+                                             cudaStream_t);
+
+// float flags -> byte flags (once per fused step).  With `changed` the kernel also reports whether any
+// byte differs from what the destination held (the step keeps its byte copy and the clearance field
+// between calls and rebuilds the latter only then).
+__global__ void k_flags_to_u8(const float* __restrict__ f, unsigned char* __restrict__ o, long long n,
+                              int* __restrict__ changed) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) o[t] = (unsigned char)(((int)f[t]) & 0xFF);
+  if (t >= n) return;
+  const unsigned char v = (unsigned char)(((int)f[t]) & 0xFF);
+  if (changed && o[t] != v) *changed = 1;
+  o[t] = v;
 }
 // 16 cells per thread: four 16-byte loads, one 16-byte store.
-__global__ void k_flags_to_u8_x16(const float4* __restrict__ f, uint4* __restrict__ o, long long n16) {
+__global__ void k_flags_to_u8_x16(const float4* __restrict__ f, uint4* __restrict__ o, long long n16,
+                                  int* __restrict__ changed) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n16) return;
   unsigned w[4];
@@ -1053,15 +1264,19 @@ __global__ void k_flags_to_u8_x16(const float4* __restrict__ f, uint4* __restric
     w[q] = (unsigned)(((int)v.x) & 0xFF) | ((unsigned)(((int)v.y) & 0xFF) << 8) |
            ((unsigned)(((int)v.z) & 0xFF) << 16) | ((unsigned)(((int)v.w) & 0xFF) << 24);
   }
+  if (changed) {
+    const uint4 old = o[t];
+    if (old.x != w[0] || old.y != w[1] || old.z != w[2] || old.w != w[3]) *changed = 1;
+  }
   o[t] = make_uint4(w[0], w[1], w[2], w[3]);
 }
-void launch_flags_to_u8(const float* f, unsigned char* o, long long n, cudaStream_t st) {
+void launch_flags_to_u8(const float* f, unsigned char* o, long long n, int* changed, cudaStream_t st) {
   if (n % 16 == 0 && ((size_t)f % 16) == 0 && ((size_t)o % 16) == 0) {
     const long long n16 = n / 16;
-    k_flags_to_u8_x16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const float4*)f, (uint4*)o, n16);
+    k_flags_to_u8_x16<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>((const float4*)f, (uint4*)o, n16, changed);
     return;
   }
-  k_flags_to_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, o, n);
+  k_flags_to_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, o, n, changed);
 }
 
 }  // namespace tfl
