@@ -47,6 +47,45 @@ ALGO_BYTES = {
 }
 
 
+def use_all_host_cores():
+    """The CPU arm uses every host core whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1)."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)      # the runtime may already be initialised
+    except OSError:
+        pass
+    return n
+
+
+def ncu_traffic(kernel_regexes, path=None):
+    """dram read + write bytes per launch of the named kernels, summed, from the tracked ncu raw table of the
+    current build (profiles/r02_advect_ncu_raw.csv: `ncu -i ... --page raw --csv`); None when absent."""
+    import csv
+    import re
+    path = path or os.path.join(ROOT, "profiles", "r02_advect_ncu_raw.csv")
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    hdr = next((r for r in rows if "Kernel Name" in r), None)
+    if hdr is None:
+        return None, None
+    ki = hdr.index("Kernel Name")
+    cols = [i for i, h in enumerate(hdr) if h in ("dram__bytes_read.sum", "dram__bytes_write.sum")]
+    units = rows[rows.index(hdr) + 1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for rx in kernel_regexes:
+        vals = []
+        for r in rows[rows.index(hdr) + 2:]:
+            if len(r) > ki and re.search(rx, r[ki]):
+                vals.append(sum(float(r[i].replace(",", "")) * scale.get(units[i], 1.0) for i in cols))
+        if not vals:
+            return None, None
+        total += sum(vals) / len(vals)
+    return total, os.path.relpath(path, ROOT)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -93,11 +132,12 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def make_problem(n=N_GRID):
+def make_problem(n=N_GRID, velocity="smooth"):
+    """velocity: "smooth" (band-limited, +-2 cells/s) or "random" (uniform in [-2, 2] per face)."""
     import torch
     from fluidnet_b200 import synth, simulate
     flags = synth.make_flags(n, n, n, True, nb=1, geometry=True)
-    U = synth.make_smooth_velocity(flags, True, amp=2.0)
+    U = (synth.make_smooth_velocity if velocity == "smooth" else synth.make_velocity)(flags, True, amp=2.0)
     density = synth.make_density(flags)
     batch = {"pDiv": np.zeros_like(flags), "UDiv": U, "flags": flags, "density": density}
     # Plume inflow BCs from the product's own host mirror of tfluids.createPlumeBCs (lib/simulate.lua:47-123);
@@ -132,6 +172,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_cores()
     import oracle
     oracle.build()
     be = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
@@ -258,40 +299,57 @@ def main():
         # L2 flush buffer (> 126 MB) written between timed iterations.
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
-        def step():
-            simulate.simulate_fused(None, mconf, gb, gm)
+        def timed_steps(state, steps, warmup):
+            """Per-step CUDA events on the launch stream, L2 flushed before each step; returns total ms."""
+            for _ in range(warmup):
+                simulate.simulate_fused(None, mconf, state, gm)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            evs = []
+            lc0 = ctx.launch_count()
+            for _ in range(steps):
+                flush.fill_(0.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                simulate.simulate_fused(None, mconf, state, gm)
+                e1.record(stream)
+                evs.append((e0, e1))
+            stream.synchronize()
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs), ctx.launch_count() - lc0
 
-        for _ in range(max(args.warmup, 3)):
-            step()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        l0 = ctx.launch_count()
-        evs = []
-        for _ in range(args.steps):
-            flush.fill_(0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step()
-            e1.record(stream)
-            evs.append((e0, e1))
-        stream.synchronize()
-        torch.cuda.synchronize()
-        launches = ctx.launch_count() - l0
+        total_ms, launches = timed_steps(gb, args.steps, max(args.warmup, 3))
+        # trace-length regime of the timed steps (the advection cost is data dependent)
+        max_u_dt = float(gb["UDiv"].abs().max().item()) * mconf["dt"]
         if world > 1:
             dist.barrier()
         if rank == 0:
             sampler.stop_flag.set()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t.item()
         assert ctx.trace_faults() == 0, "line traces left the domain / hit a hard-error path"
+
+        # ---- SURVEY.md 8(d) variant: uniform-random +-2 velocity (incoherent gathers), same step ----
+        variant = None
+        if not args.no_extra:
+            b_r, _, _ = make_problem(n, velocity="random")
+            g_r = {k: torch.from_numpy(v.copy()).cuda() for k, v in b_r.items()}
+            vsteps = max(3, min(args.steps, 10))
+            ms_r, _ = timed_steps(g_r, vsteps, 3)
+            tr = torch.tensor([ms_r], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            variant = {"velocity": "uniform random in [-2, 2] cells/s per face at step 0 (SURVEY.md 8d)",
+                       "value": world * 1000.0 * vsteps / tr.item(), "unit": "steps/s", "steps": vsteps,
+                       "max_u_dt_cells": float(g_r["UDiv"].abs().max().item()) * mconf["dt"]}
+            del g_r
 
         # ---- e2e: host buffers through the C-ABI host-sim call -----------------------------
         import ctypes as C
@@ -343,6 +401,7 @@ def main():
         k_ms = float(np.mean([a.elapsed_time(b) for a, b in ks]))
         algo_bytes = ALGO_BYTES["advect_vel"] * n ** 3
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic([r"k_advect_vel_pass1", r"k_advect_vel_pass2"]) if n == 128 else (None, None)
 
         # ---- BASELINE config 4: 100-iteration Jacobi sweep (stencil HBM roofline) ----------
         extra = []
@@ -396,18 +455,23 @@ def main():
         return 0
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
+        use_all_host_cores()
         import oracle
         be = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
         b2, m2, _ = make_problem(n)
-        t0 = time.perf_counter()
-        cpu_step_ops(be, b2, m2, None)
-        t1 = time.perf_counter() - t0
+        ts = []
+        for it in range(4):                    # 1 warm-up + 3 timed steps, median
+            t0 = time.perf_counter()
+            cpu_step_ops(be, b2, m2, None)
+            if it > 0:
+                ts.append(time.perf_counter() - t0)
+        t1 = float(np.median(ts))
         cpu = {"value": 1.0 / t1, "unit": "steps/s", "cores": be.num_threads(),
                "kind": "reference" if be.name == "reference" else "port",
-               "sample": "1 full %d^3 step of the reference CPU operators (advection, BCs, buoyancy, "
-                         "vorticity, wall BCs, divergence, velocity update; CNN conv stack replaced by 1 "
-                         "Jacobi sweep: no CPU conv source in the reference)" % n}
+               "sample": "median of 3 full %d^3 steps (after 1 warm-up) of the reference CPU operators (advection, "
+                         "BCs, buoyancy, vorticity, wall BCs, divergence, velocity update; CNN conv stack replaced "
+                         "by 1 Jacobi sweep: no CPU conv source in the reference)" % n}
 
     ms = total_ms / args.steps
     line = {
@@ -419,18 +483,19 @@ def main():
                                "BCs + buoyancy + vorticity confinement + CNN projection (3-D default net), "
                                "1 tfluids.simulate per step" % n,
                    "grid": [n, n, n], "batch_per_gpu": 1, "parallelism": "independent grid per GPU",
-                   "l2": "256 MB buffer written between timed steps (L2 flush)"},
+                   "l2": "256 MB buffer written between timed steps (L2 flush)",
+                   "velocity": "band-limited (4 Fourier modes per component), +-2 cells/s at step 0",
+                   "max_u_dt_cells_at_end": max_u_dt},
+        "variant_random_velocity": variant,
         "hbm_gbs_algorithmic": BYTES_PER_VOXEL_STEP * n ** 3 / (ms * 1e-3) / 1e9,
         "e2e": {"value": world * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": bytes_io,
                 "d2h_bytes_per_step": bytes_io},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "advectVel (k_advect_vel_pass1+pass2, maccormackOurs)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 84.9e6 if n == 128 else None,   # ncu dram read+write, both passes (profiles/r01_ncu_summary.md)
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms,
-                     # ncu (profiles/r01_ncu_summary.md): this kernel pair is bound by instruction issue
-                     # (sm__issue_active 62-70 %, DRAM 4 %), so the HBM fraction is small by nature.
-                     "limiter": "instruction issue (ncu sm__issue_active 62-70 %, dram 4 %)"},
+                     "limiter": "instruction issue (ncu tables under profiles/)"},
         "roofline_extra": extra,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),

@@ -80,6 +80,19 @@ struct tfl_cnn {
   ConvTcGeo act_geo = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
+
+// Every entry point runs on the context's device whatever the caller's current device is, and leaves the
+// caller's current device as it found it (a host with several contexts / GPUs in one thread).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const tfl_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 namespace {
 
 int fail(tfl_ctx* ctx, const char* fmt, ...) {
@@ -250,6 +263,9 @@ int tfl_create(tfl_ctx** out, int device) {
   *out = nullptr;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return 1;
+  int prev_dev = device;
+  cudaGetDevice(&prev_dev);
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore_{prev_dev};   // caller's device stays current
   if (cudaSetDevice(device) != cudaSuccess) return 1;
   tfl_ctx* c = new tfl_ctx();
   c->device = device;
@@ -272,6 +288,7 @@ int tfl_create(tfl_ctx** out, int device) {
 }
 
 void tfl_destroy(tfl_ctx* ctx) {
+  DeviceGuard guard_(ctx);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -293,6 +310,7 @@ void tfl_destroy(tfl_ctx* ctx) {
 const char* tfl_last_error(const tfl_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
 int tfl_set_stream(tfl_ctx* ctx, void* s) {
+  DeviceGuard guard_(ctx);
   if (!ctx) return 1;
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (s == nullptr) {
@@ -309,12 +327,14 @@ int tfl_set_stream(tfl_ctx* ctx, void* s) {
 }
 void* tfl_get_stream(tfl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int tfl_sync(tfl_ctx* ctx) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int64_t tfl_launch_count(const tfl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset) {
+  DeviceGuard guard_(ctx);
   unsigned long long v = 0;
   TFL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -324,6 +344,7 @@ int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset) {
 }
 
 int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo, int32_t z_hi) {
+  DeviceGuard guard_(ctx);
   if (global_nz <= 0) { ctx->slab = false; return 0; }
   ctx->slab = true;
   ctx->zoff = z_offset; ctx->gnz = global_nz; ctx->zlo = z_lo; ctx->zhi = z_hi;
@@ -331,36 +352,44 @@ int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo
 }
 
 int tfl_set_slab_margin(tfl_ctx* ctx, int32_t planes) {
+  DeviceGuard guard_(ctx);
   if (planes < 0) return fail(ctx, "slab margin must be >= 0");
   ctx->slab_margin = planes;
   return 0;
 }
 
 int tfl_alloc(tfl_ctx* ctx, size_t bytes, void** p) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaMalloc(p, bytes));
   return 0;
 }
 int tfl_free(tfl_ctx* ctx, void* p) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaFree(p));
   return 0;
 }
 int tfl_alloc_host(tfl_ctx* ctx, size_t bytes, void** p) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaMallocHost(p, bytes));
   return 0;
 }
 int tfl_free_host(tfl_ctx* ctx, void* p) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaFreeHost(p));
   return 0;
 }
 int tfl_memcpy_h2d(tfl_ctx* ctx, void* d, const void* h, size_t bytes) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int tfl_memcpy_d2h(tfl_ctx* ctx, void* h, const void* d, size_t bytes) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 int tfl_memcpy_d2d(tfl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  DeviceGuard guard_(ctx);
   TFL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
@@ -369,6 +398,7 @@ int tfl_memcpy_d2d(tfl_ctx* ctx, void* dst, const void* src, size_t bytes) {
 // Operators
 // ---------------------------------------------------------------------------------------
 int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags")) return 1;
   if (!((!is_3d || (ctx->slab ? ctx->gnz : flags->nz) >= bnd * 2 + 1) && flags->ny >= bnd * 2 + 1 &&
         flags->nx >= bnd * 2 + 1))
@@ -381,6 +411,7 @@ int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd) {
 }
 
 int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* occ, int64_t* bad) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, occ, "occupancy")) return 1;
   if (!same_spatial(flags, occ)) return fail(ctx, "Size mismatch");
   const long long n = (long long)flags->nb * flags->nz * flags->ny * flags->nx;
@@ -398,6 +429,7 @@ int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* 
 }
 
 int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   Geo g;
   if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
@@ -408,6 +440,7 @@ int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* fl
 
 int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
                                     const tfl_grid* div) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, div, "UDiv")) return 1;
   if (!same_spatial(flags, div)) return fail(ctx, "Size mismatch");
   Geo g;
@@ -418,6 +451,7 @@ int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_g
 }
 
 int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p")) return 1;
   if (!same_spatial(flags, p)) return fail(ctx, "Size mismatch");
   Geo g;
@@ -429,6 +463,7 @@ int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid*
 
 int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* density,
                      const float gravity[3], float dt) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, density, "density"))
     return 1;
   if (!same_spatial(flags, density)) return fail(ctx, "Size mismatch");
@@ -444,6 +479,7 @@ int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, con
 }
 
 int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const float gravity[3], float dt) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   if (!gravity) return fail(ctx, "gravity must be a 3D vector (even in 2D).");
   Geo g;
@@ -456,6 +492,7 @@ int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, cons
 }
 
 int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, float strength) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   Geo g;
   if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
@@ -471,6 +508,7 @@ int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* f
 
 int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid* U, const tfl_grid* flags,
                       int method, int sample_outside_fluid, float strength, const tfl_grid* s_dst) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, s, "s") || check_vel(ctx, U, flags)) return 1;
   if (!same_spatial(flags, s)) return fail(ctx, "Size mismatch");
   if (s_dst && (check_scalar(ctx, s_dst, "sDst") || !same_spatial(s_dst, s))) return fail(ctx, "Size mismatch");
@@ -510,6 +548,7 @@ int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid*
 
 int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* flags, int method,
                    float strength, const tfl_grid* U_dst) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   if (U_dst && (check_vel(ctx, U_dst, flags) || U_dst->nc != U->nc)) return fail(ctx, "Size mismatch");
   if (method < 0 || method > 5) return fail(ctx, "advection method not supported");
@@ -546,6 +585,7 @@ int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* fl
 int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags,
                                    const tfl_grid* div, int is_3d, float p_tol, int max_iter,
                                    float* residual, int* iterations) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
   if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -607,6 +647,7 @@ int tfl_precond_from_string(const char* name) {
 int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, const tfl_grid* div,
                                 int is_3d, int precond, float tol, int max_iter, float* residual,
                                 int* iterations) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
   if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -624,6 +665,7 @@ int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
 }
 
 int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, int is_3d) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p")) return 1;
   if (!same_spatial(flags, p)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -637,6 +679,7 @@ int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
 }
 
 int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* out) {
+  DeviceGuard guard_(ctx);
   if (!in || !out || !in->data || !out->data) return fail(ctx, "ERROR: input and output must be dim 5");
   if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
   if (out->nb != in->nb || out->nc != in->nc || out->nz != in->nz * ratio || out->ny != in->ny * ratio ||
@@ -648,6 +691,7 @@ int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tf
 }
 
 int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst) {
+  DeviceGuard guard_(ctx);
   if (!src || !dst || !src->data || !dst->data) return fail(ctx, "ERROR: src and dst must be dim 5");
   if (!same_spatial(src, dst) || src->nc != dst->nc) return fail(ctx, "size mismatch");
   if (blur_rad <= 0) return fail(ctx, "blurRad must be a positive, non-zero integer");   // init.lua:586-587
@@ -672,6 +716,7 @@ int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is
 }
 
 int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_rad, int is_3d, const tfl_grid* dst) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, dst, "dst")) return 1;
   if (!same_spatial(flags, dst)) return fail(ctx, "size mismatch");
   if (search_rad <= 0) return fail(ctx, "searchRad must be a positive, non-zero integer");   // init.lua:609-610
@@ -684,6 +729,7 @@ int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_ra
 
 int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* go,
                                      const tfl_grid* gU) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, go, "gradOutput")) return 1;
   if (!gU || !gU->data || gU->nc != U->nc || !same_spatial(gU, U) || !same_spatial(go, flags)) return fail(ctx, "Size mismatch");
   if (ctx->slab) return fail(ctx, "backward operators: single GPU only");
@@ -695,6 +741,7 @@ int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_
 
 int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p,
                                  const tfl_grid* go, const tfl_grid* gp) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p") ||
       check_scalar(ctx, gp, "gradP"))
     return 1;
@@ -709,6 +756,7 @@ int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid
 
 int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* go,
                                                 const tfl_grid* gi) {
+  DeviceGuard guard_(ctx);
   if (!in || !go || !gi || !in->data || !go->data || !gi->data)
     return fail(ctx, "ERROR: input, gradOutput and gradInput must be dim 5");
   if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
@@ -723,18 +771,21 @@ int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const t
 
 // Debug hook (not in include/tfl.h): planes per CTA of the PCG sweep pipeline.
 extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
+  DeviceGuard guard_(ctx);
   if (!ctx) return 1;
   ctx->pcg.groups_override = groups;
   return 0;
 }
 
 extern "C" int tfl_debug_pcg_timing(tfl_ctx* ctx, void* dev_buf) {
+  DeviceGuard guard_(ctx);
   if (!ctx) return 1;
   ctx->pcg.debug_timing = dev_buf;
   return 0;
 }
 
 int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc) {
+  DeviceGuard guard_(ctx);
   if (!x || !inv_mask || !bc || !x->data || !inv_mask->data || !bc->data) return fail(ctx, "applyBC: nil tensor");
   if (!same_spatial(x, inv_mask) || !same_spatial(x, bc) || x->nc != inv_mask->nc || x->nc != bc->nc)
     return fail(ctx, "Size mismatch");
@@ -745,6 +796,7 @@ int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, cons
 }
 
 int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
+  DeviceGuard guard_(ctx);
   if (!x || !x->data) return fail(ctx, "clamp: nil tensor");
   const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
   launch_clamp(x->data, lo, hi, n, ctx->stream);
@@ -758,6 +810,7 @@ int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
 int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, const int32_t* cout,
                    const int32_t* ksize, const float* const* weights, const float* const* biases,
                    tfl_cnn** out) {
+  DeviceGuard guard_(ctx);
   return tfl_cnn_create_graph(ctx, is_3d, n_layers, cin, cout, ksize, nullptr, nullptr, 0, 0, weights, biases, out);
 }
 
@@ -765,6 +818,7 @@ int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* c
                          const int32_t* ksize, const int32_t* pool, const int32_t* up, int pool_is_max,
                          int nonlin_sigmoid, const float* const* weights, const float* const* biases,
                          tfl_cnn** out) {
+  DeviceGuard guard_(ctx);
   if (!out || n_layers < 1) return fail(ctx, "cnn: bad arguments");
   // Channels the convolution of layer l really emits: cout * up^d (ConvolutionUpsample, model_utils.lua:74-76).
   std::vector<int32_t> cout_conv(n_layers);
@@ -853,6 +907,7 @@ int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* c
 }
 
 int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
+  DeviceGuard guard_(ctx);
   if (!m || mode < 0 || mode > 2) return fail(ctx, "cnn_set_mode: bad arguments");
   if (mode > 0 && !m->tc_ok)
     return fail(ctx, "cnn_set_mode: the tensor-core path covers the 3-D 'default' architecture only");
@@ -867,6 +922,7 @@ int tfl_debug_conv_timestamps(void* dev_buf) { conv_tc_set_debug((long long*)dev
 int tfl_debug_conv_ts_counters(void* dev_buf) { conv_ts_set_debug((long long*)dev_buf); return 0; }
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
+  DeviceGuard guard_(ctx);
   if (!m) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (float* p : m->w) cudaFree(p);
@@ -1011,6 +1067,7 @@ static size_t cnn_scratch_bytes(const tfl_cnn* m, const Geo& g) {
 int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_grid* U_div,
                     const tfl_grid* flags, const tfl_grid* p_out, const tfl_grid* U_out, float threshold,
                     float* scale_out) {
+  DeviceGuard guard_(ctx);
   if (!m) return fail(ctx, "cnn is nil");
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U_div, flags) ||
       check_scalar(ctx, p_out, "p") || check_vel(ctx, U_out, flags))
@@ -1042,6 +1099,7 @@ int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_g
 //                              least 4 planes away from a local end that is not a global end.
 int tfl_cnn_stats(tfl_ctx* ctx, const tfl_grid* U_div, const tfl_grid* flags, const tfl_grid* U1,
                   double* dev_sums) {
+  DeviceGuard guard_(ctx);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U_div, flags) || check_vel(ctx, U1, flags)) return 1;
   if (!dev_sums) return fail(ctx, "cnn_stats: nil sums");
   Geo g;
@@ -1060,6 +1118,7 @@ int tfl_cnn_stats(tfl_ctx* ctx, const tfl_grid* U_div, const tfl_grid* flags, co
 int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_grid* U1,
                               const tfl_grid* flags, const double* dev_sums, const tfl_grid* p_out,
                               const tfl_grid* U_out, float threshold) {
+  DeviceGuard guard_(ctx);
   if (!m) return fail(ctx, "cnn is nil");
   if (!m->tc_ok || m->mode == 0) return fail(ctx, "cnn_project_from_sums needs the tensor-core path (3-D default net)");
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U1, flags) ||
@@ -1202,6 +1261,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
 }
 
 int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl_cnn* cnn) {
+  DeviceGuard guard_(ctx);
   if (!s || !mc) return fail(ctx, "simulate: nil state / mconf");
   if (check_scalar(ctx, &s->flags, "flags") || check_scalar(ctx, &s->p, "pDiv") || check_vel(ctx, &s->U, &s->flags))
     return 1;
@@ -1280,6 +1340,7 @@ struct tfl_host_sim {
 int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_t nx, int is_3d,
                         const float* flags, const float* U_bc, const float* U_bc_inv, const float* d_bc,
                         const float* d_bc_inv, tfl_host_sim** out) {
+  DeviceGuard guard_(ctx);
   if (!out || !flags) return fail(ctx, "host_sim: bad arguments");
   tfl_host_sim* hs = new tfl_host_sim();
   memset(&hs->st, 0, sizeof(hs->st));
@@ -1309,6 +1370,7 @@ int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_
 }
 
 void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs) {
+  DeviceGuard guard_(ctx);
   if (!hs) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (void* p : hs->owned) cudaFree(p);
@@ -1317,6 +1379,7 @@ void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs) {
 
 int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
                       const tfl_mconf* mc, tfl_cnn* cnn) {
+  DeviceGuard guard_(ctx);
   if (!hs || !p || !U) return fail(ctx, "host_sim_step: nil buffer");
   cudaStream_t st = ctx->stream;
   tfl_state s = hs->st;

@@ -162,11 +162,8 @@ __device__ __forceinline__ FluidVal fluid_val(const float* __restrict__ blk,
   return FluidVal{__ldg(blk + o), (flag_at(fl, o) & kFluid) != 0};
 }
 template <typename FT>
-__device__ __forceinline__ float lerp_block_fluid(const float* __restrict__ blk,
-                                                  const FT* __restrict__ fl, const Geo& g,
-                                                  V3 pos) {
-  const Lerp q = build_index(g, pos);
-  const int o = corner(g, q);
+__device__ __forceinline__ float lerp_fluid_at(const float* __restrict__ blk, const FT* __restrict__ fl,
+                                               const Geo& g, const Lerp& q, int o) {
   const int sy = g.nx, sz = g.nx * g.ny;
   FluidVal all;
   const FluidVal ab = pair_fluid(fluid_val(blk, fl, o), fluid_val(blk, fl, o + sy), q.t0, q.t1);
@@ -181,6 +178,13 @@ __device__ __forceinline__ float lerp_block_fluid(const float* __restrict__ blk,
     all = abcd;
   }
   return all.ok ? all.v : lerp_at(blk, g, q, o);
+}
+template <typename FT>
+__device__ __forceinline__ float lerp_block_fluid(const float* __restrict__ blk,
+                                                  const FT* __restrict__ fl, const Geo& g,
+                                                  V3 pos) {
+  const Lerp q = build_index(g, pos);
+  return lerp_fluid_at(blk, fl, g, q, corner(g, q));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -307,9 +311,11 @@ __device__ inline bool ray_border(const Geo& g, V3 pos, V3 next, V3* ip) {
 }
 
 // Returns true if the trace was cut short (geometry or domain border).
+// Out of line on purpose: the kernels that trace keep their common (clear-space) path compact enough
+// for the instruction cache, and only cells near solids / the border pay for the call.
 template <typename FT>
-__device__ inline bool line_trace(const FT* __restrict__ fl, const Geo& g, V3 pos, V3 delta,
-                                  V3* out) {
+__device__ __noinline__ bool line_trace(const FT* __restrict__ fl, const Geo& g, V3 pos, V3 delta,
+                                        V3* out) {
   *out = pos;
   const float length = norm3(delta);
   if (length <= TFL_TRACE_EPS) return false;
@@ -354,15 +360,20 @@ __device__ inline bool line_trace(const FT* __restrict__ fl, const Geo& g, V3 po
 }
 
 // ---------------------------------------------------------------------------------------
-// Clear-space fast path.  clear[c] = largest r <= kClearMax such that every cell within
-// Chebyshev distance r of c lies inside the local storage and is fluid (0: no guarantee; 2-D
-// grids ignore z).  A trace of length < r that starts at the centre of c never meets a
-// non-fluid cell or the domain border, its interpolation footprint needs no index clamp and
-// no slab-range test: the code below is line_trace / build_index / lerp_at with the branches
-// that cannot fire removed -- the arithmetic, and its order, are unchanged (bit-identical).
+// Clear-space fast path.  clear[c] = Chebyshev distance (in cells, capped at kClearMax + 1) from cell c to
+// the nearest cell that is not fluid or lies on an end of the LOCAL storage; 0 for such cells themselves
+// (2-D grids ignore z).  A trace of length < clear - 0.5 that starts at the centre of c stays inside
+// fluid cells of the domain interior (the nearest solid face is clear - 0.5 away), the 2x2x2
+// interpolation footprint of its end point and the MacCormack clamp boxes lie inside the storage without
+// any index clamp, and a trace shorter than clear - 1 only has fluid cells in that footprint.  The code
+// below is line_trace / build_index / lerp_at with the branches that then cannot fire removed -- the
+// arithmetic, and its order, are unchanged (bit-identical).
 // ---------------------------------------------------------------------------------------
 constexpr int kClearMax = 7;
 #define TFL_CLEAR_SLACK 0.01f      // covers |dir| <= 1 + ulps and the accumulated step rounding
+// longest trace that stays in clear space / whose interpolation footprint is all fluid
+__device__ __forceinline__ float clear_reach(int clr) { return (float)clr - (0.5f + TFL_CLEAR_SLACK); }
+__device__ __forceinline__ float clear_reach_fluid(int clr) { return (float)clr - (1.0f + TFL_CLEAR_SLACK); }
 
 __device__ __forceinline__ V3 line_trace_clear(V3 pos, V3 delta, float length) {
   V3 out = pos;
@@ -386,10 +397,21 @@ __device__ __forceinline__ int build_index_clear(const Geo& g, V3 pos, Lerp& q) 
   q.f1 = pz - (float)q.zi; q.f0 = 1.0f - q.f1;
   return cell(g, g.is3d ? q.zi - g.zoff : 0, q.yi, q.xi);
 }
+// interpolWithFluid on a footprint that needs no index clamp (flags still decide which corners count)
+template <typename FT>
+__device__ __forceinline__ float lerp_block_fluid_noclamp(const float* __restrict__ blk, const FT* __restrict__ fl,
+                                                          const Geo& g, V3 pos);
 __device__ __forceinline__ float lerp_block_clear(const float* __restrict__ blk, const Geo& g, V3 pos) {
   Lerp q;
   const int o = build_index_clear(g, pos, q);
   return lerp_at(blk, g, q, o);
+}
+template <typename FT>
+__device__ __forceinline__ float lerp_block_fluid_noclamp(const float* __restrict__ blk, const FT* __restrict__ fl,
+                                                          const Geo& g, V3 pos) {
+  Lerp q;
+  const int o = build_index_clear(g, pos, q);
+  return lerp_fluid_at(blk, fl, g, q, o);
 }
 
 // ---------------------------------------------------------------------------------------

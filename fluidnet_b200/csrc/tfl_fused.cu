@@ -16,6 +16,7 @@
 //                                                             (lib/model.lua:86-150)
 //   k_cnn_finish_fused   VelocityUpdate, ApplyScale, SetWallBcs (lib/model.lua:380-390)
 //                        setConstVals (U) ; U:clamp(-1e6, 1e6) (lib/simulate.lua:321, :326)
+#include <initializer_list>
 #include "tfl_device.cuh"
 #include "tfl_kernels.h"
 
@@ -47,7 +48,10 @@ __global__ void k_post_advect(const float* __restrict__ tmp_s, const float* __re
   float rc = 0.0f;
   if (density) {
     rc = bc_apply(__ldg(tmp_s + sb + c), bc.d_inv, bc.d_bc, sb + c);
-    density[sb + c] = rc;
+    // The loop applies setConstVals to the density two more times before the step ends
+    // (lib/simulate.lua:252, :321) and nothing else writes it: store the final value (equal to rc for
+    // idempotent BCs such as the plume's), the buoyancy below reads the first application.
+    density[sb + c] = bc_apply(bc_apply(rc, bc.d_inv, bc.d_bc, sb + c), bc.d_inv, bc.d_bc, sb + c);
   }
   float u[3];
   for (int a = 0; a < g.nc; a++) u[a] = bc_apply(__ldg(tmp_u + ub + a * g.n + c), bc.u_inv, bc.u_bc, ub + a * g.n + c);
@@ -298,7 +302,20 @@ __global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ 
   };
   if (density) {
     dens_bc(sb + c0, rc);
-    st4(density + sb + c0, rc);
+    float fin[4] = {rc[0], rc[1], rc[2], rc[3]};
+    if (bc.d_inv) {        // second and third setConstVals of the step (lib/simulate.lua:252, :321)
+      float iv[4], bv[4];
+      ld4(bc.d_inv + sb + c0, iv);
+      ld4(bc.d_bc + sb + c0, bv);
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        float t = fin[v] * iv[v];
+        t = t + bv[v];
+        t = t * iv[v];
+        fin[v] = t + bv[v];
+      }
+    }
+    st4(density + sb + c0, fin);
   }
   float u[3][4];
 #pragma unroll
@@ -680,6 +697,13 @@ static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
   grid = dim3((quads + bx - 1) / bx, (g.ny + by - 1) / by, ((long long)g.nb * g.nz + bz - 1) / bz);
   return true;
 }
+// The quad kernels use 16-byte accesses on caller-owned pointers: every one must be 16-byte aligned
+// (null = absent), otherwise the scalar kernels run.
+static inline bool aligned16(std::initializer_list<const void*> ptrs) {
+  for (const void* p : ptrs)
+    if (((uintptr_t)p & 15u) != 0) return false;
+  return true;
+}
 #define TFL_LAUNCH4F(kernel, g, grid_, block_, st, ...)                            \
   do {                                                                              \
     if ((g).is3d) kernel<true><<<grid_, block_, 0, st>>>(__VA_ARGS__);              \
@@ -698,7 +722,7 @@ static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
 bool launch_vort_curl_quad(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
                            cudaStream_t st) {
   dim3 qg, qb;
-  if (!quad_dims(g, qg, qb)) return false;
+  if (!quad_dims(g, qg, qb) || !aligned16({U, curl, cnorm, force})) return false;
   TFL_LAUNCH4F(k_vort_curl4, g, qg, qb, st, U, curl, cnorm, g);
   TFL_LAUNCH4F(k_vort_force4, g, qg, qb, st, curl, cnorm, force, strength, g);
   return true;
@@ -709,7 +733,7 @@ void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned c
                         int do_buoy, const float s[3], const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, d_inv, d_bc};
   dim3 qg, qb;
-  if (quad_dims(g, qg, qb)) {
+  if (quad_dims(g, qg, qb) && aligned16({tmp_s, tmp_u, flags, density, U, u_inv, u_bc, d_inv, d_bc})) {
     TFL_LAUNCH4F(k_post_advect4, g, qg, qb, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
     return;
   }
@@ -720,7 +744,7 @@ void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* forc
                          const Geo& g, cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
   dim3 qg, qb;
-  if (quad_dims(g, qg, qb)) {
+  if (quad_dims(g, qg, qb) && aligned16({U, flags, force, u_inv, u_bc})) {
     TFL_LAUNCH4F(k_vort_bc_mask4, g, qg, qb, st, U, flags, force, do_vort, bc, mask_mode, sums, g);
     return;
   }
@@ -730,7 +754,7 @@ void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
                              cudaStream_t st) {
   dim3 qg, qb;
-  if (quad_dims(g, qg, qb)) {
+  if (quad_dims(g, qg, qb) && aligned16({p_div, U1, flags, x0})) {
     TFL_LAUNCH4F(k_cnn_inputs_fused4, g, qg, qb, st, p_div, U1, flags, sums, threshold, scale_out, (float4*)x0, px, py, g);
     return;
   }
@@ -741,7 +765,7 @@ void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* 
                              cudaStream_t st) {
   BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
   dim3 qg, qb;
-  if (quad_dims(g, qg, qb)) {
+  if (quad_dims(g, qg, qb) && aligned16({p_net, U, flags, p_out, u_inv, u_bc})) {
     TFL_LAUNCH4F(k_cnn_finish_fused4, g, qg, qb, st, p_net, U, flags, scale, p_out, bc, lo, hi, g);
     return;
   }

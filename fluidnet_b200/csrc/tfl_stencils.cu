@@ -10,6 +10,7 @@
 //   addGravity     third_party/tfluids.cc:1239-1306  vorticity   third_party/tfluids.cc:1312-1458
 //   Jacobi         generic/tfluids.cu:1765-1927      emptyDomain generic/tfluids.cc:136-172
 //   flagsToOccupancy generic/tfluids.cu:355-401
+#include <algorithm>
 #include "tfl_device.cuh"
 #include "tfl_kernels.h"
 
@@ -304,15 +305,16 @@ __device__ __forceinline__ float advect_scalar_cell(const FT* __restrict__ fl, c
 template <typename FT>
 __device__ __forceinline__ float advect_scalar_cell_clear(const FT* __restrict__ fl, const float* __restrict__ ub,
                                                           const float* __restrict__ src, const Geo& g, float dt,
-                                                          int k, int j, int i, bool outside, float reach,
+                                                          int k, int j, int i, bool outside, int clr,
                                                           V3* pos_out) {
   const V3 start = {(float)i + 0.5f, (float)j + 0.5f, (float)(k + g.zoff) + 0.5f};
   const V3 delta = scale3(mac_centered(ub, g, k, j, i), -dt);
   const float length = norm3(delta);
-  if (length < reach) {
+  if (length < clear_reach(clr)) {
     const V3 back = line_trace_clear(start, delta, length);
     if (pos_out) *pos_out = back;
-    return lerp_block_clear(src, g, back);
+    if (outside || length < clear_reach_fluid(clr)) return lerp_block_clear(src, g, back);
+    return lerp_block_fluid_noclamp(src, fl, g, back);       // a solid cell may be in the footprint
   }
   V3 back;
   line_trace(fl, g, start, delta, &back);
@@ -335,7 +337,7 @@ __global__ void k_advect_scalar_pass1(const float* __restrict__ s, const float* 
   const int clr = (kTraced && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
   if (clr > 0) {
     v = advect_scalar_cell_clear(flags + b * g.n, U + (long long)b * g.nc * g.n, s + b * g.n, g, dt, k, j, i,
-                                 outside != 0, (float)clr - TFL_CLEAR_SLACK, pos_out ? &pos : nullptr);
+                                 outside != 0, clr, pos_out ? &pos : nullptr);
   } else if (!on_border(g, k, j, i)) {
     v = advect_scalar_cell<METHOD>(flags + b * g.n, U + (long long)b * g.nc * g.n, s + b * g.n, g, dt, k,
                                    j, i, outside != 0, pos_out ? &pos : nullptr);
@@ -370,7 +372,7 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
   float bw = 0.0f;
   if (clr > 0)
     bw = advect_scalar_cell_clear(fl, U + (long long)b * g.nc * g.n, fb, g, -dt, k, j, i, outside != 0,
-                                  (float)clr - TFL_CLEAR_SLACK, nullptr);
+                                  clr, nullptr);
   else if (!border)
     bw = advect_scalar_cell<TFL_ADVECT_MACCORMACK_OURS>(fl, U + (long long)b * g.nc * g.n, fb, g, -dt, k,
                                                         j, i, outside != 0, nullptr);
@@ -394,8 +396,8 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
       // 27 (9 in 2-D) neighbours sit at fixed offsets from the centre.
       const int ctr = cell(g, g.is3d ? kl0 : 0, j0, i0);
       const int sy = g.nx, sz = g.nx * g.ny;
-      // clearance >= 1 at the centre of the neighbourhood: all of it is fluid, no flag is read
-      const bool all_fluid = outside || (cl && __ldg(cl + ctr) > 0);
+      // clearance >= 2 at the centre of the neighbourhood: all of it is fluid, no flag is read
+      const bool all_fluid = outside || (cl && __ldg(cl + ctr) > 1);
       if (all_fluid) {
         found = 1;
 #pragma unroll
@@ -609,10 +611,10 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB1) k_advect_vel_pass1(cons
   const float* ub = U + (long long)b * g.nc * g.n;
   V3 v = {0.0f, 0.0f, 0.0f};
   const int clr = (OURS && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
-  if (clr > 0) {                            // fluid, interior, clear neighbourhood
+  if (clr > 0) {                            // fluid cell of the interior
     V3 vel[3];
     mac_face_velocities(ub, g, k, j, i, vel);
-    v = advect_mac_cell_clear(flags + b * g.n, vel, ub, g, dt, k, j, i, (float)clr - TFL_CLEAR_SLACK);
+    v = advect_mac_cell_clear(flags + b * g.n, vel, ub, g, dt, k, j, i, clear_reach(clr));
   } else if (!on_border(g, k, j, i)) {
     V3 vel[3];
     mac_face_velocities(ub, g, k, j, i, vel);
@@ -623,8 +625,8 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB1) k_advect_vel_pass1(cons
   if (g.is3d) ob[2 * g.n] = v.z;
 }
 
-__device__ __forceinline__ float clamp_component_mac(const float* __restrict__ orig_c, const Geo& g,
-                                                     float val, float fwd, int kglob, int j, int i, V3 vel) {
+__device__ __noinline__ float clamp_component_mac(const float* __restrict__ orig_c, const Geo& g,
+                                                  float val, float fwd, int kglob, int j, int i, V3 vel) {
   const float fi = (float)i, fj = (float)j, fk = (float)kglob;
   float lo = FLT_MAX, hi = -FLT_MAX;
   for (int l = 0; l < 2; l++) {
@@ -695,18 +697,28 @@ __global__ void __launch_bounds__(256, TFL_ADVECT_MINB2) k_advect_vel_pass2(cons
   float* db = dst + (long long)b * g.nc * g.n + c;
   const int clr = (OURS && clear) ? (int)__ldg(clear + b * g.n + c) : 0;
   if (clr > 0) {
-    // Fluid cell whose 26 neighbours are fluid: interior, no face is skipped by the correction.
-    const float reach = (float)clr - TFL_CLEAR_SLACK;
+    // Fluid cell of the interior.  clr >= 2: its 26 neighbours are fluid, no face is skipped by the
+    // correction; clr == 1: the three lower neighbours decide.
+    const float reach = clear_reach(clr);
     V3 vel[3];
     mac_face_velocities(ub, g, k, j, i, vel);
     const V3 bw = advect_mac_cell_clear(fl, vel, fb, g, -dt, k, j, i, reach);
     const float bwv[3] = {bw.x, bw.y, bw.z};
+    bool skip[3] = {false, false, false};
+    if (clr == 1) {
+      skip[0] = !(flag_at(fl, c - 1) & kFluid);
+      skip[1] = !(flag_at(fl, c - g.nx) & kFluid);
+      skip[2] = g.is3d && !(flag_at(fl, c - g.nx * g.ny) & kFluid);
+    }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       if (a < g.nc) {
         const float fw = __ldg(fb + a * g.n + c);
-        const float diff = __ldg(ub + a * g.n + c) - bwv[a];
-        float v = (float)((double)fw + ((double)strength * 0.5) * (double)diff);
+        float v = fw;
+        if (!skip[a]) {
+          const float diff = __ldg(ub + a * g.n + c) - bwv[a];
+          v = (float)((double)fw + ((double)strength * 0.5) * (double)diff);
+        }
         const V3 d = scale3(vel[a], dt);
         // |d| is the trace length of this component (the trace displacement is -d)
         if (norm3(d) < reach) v = clamp_component_mac_clear(ub + a * g.n, g, v, k, j, i, d);
@@ -1170,63 +1182,79 @@ TFL_INSTANTIATE(unsigned char)
 
 // ---------------------------------------------------------------------------------------
 // Clearance field of the advection fast path (tfl_device.cuh): three separable passes over the LOCAL
-// storage.  x: run of fluid cells around the cell; y, z: largest r such that the previous pass' value
-// is >= r on every line cell within r.
+// storage.  x: run of usable cells around the cell; y, z: largest r such that the previous pass' value
+// is >= r on every line cell within r (the box of radius r is all usable <=> the distance is r + 1).
 // ---------------------------------------------------------------------------------------
+// Grid-stride kernels on a fixed small grid: a launch whose gate word is 0 (flags unchanged) costs almost nothing.
+__device__ __forceinline__ bool clear_cell(const Geo& g, long long t, int& b, int& k, int& j, int& i) {
+  const long long total = g.n * g.nb;
+  if (t >= total) return false;
+  b = (int)(t / g.n);
+  int r = (int)(t - b * g.n);
+  k = r / (g.nx * g.ny);
+  r -= k * g.nx * g.ny;
+  j = r / g.nx;
+  i = r - j * g.nx;
+  return true;
+}
 template <typename FT>
 __global__ void k_clear_x(const FT* __restrict__ flags, unsigned char* __restrict__ out, Geo g,
                           const int* __restrict__ gate) {
-  int b, k, j, i;
   if (gate && *gate == 0) return;          // flags unchanged since the cached field was built
-  if (!thread_cell(g, b, k, j, i)) return;
-  const FT* row = flags + b * g.n + cell(g, k, j, 0);
-  int r = -1;
-  if (flag_at(row, i) & kFluid) {
-    r = 0;
-    for (int d = 1; d <= kClearMax; d++) {
-      if (i - d < 0 || i + d >= g.nx || !(flag_at(row, i - d) & kFluid) || !(flag_at(row, i + d) & kFluid)) break;
-      r = d;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;; t += (long long)gridDim.x * blockDim.x) {
+    int b, k, j, i;
+    if (!clear_cell(g, t, b, k, j, i)) return;
+    const FT* row = flags + b * g.n + cell(g, k, j, 0);
+    // usable = fluid and not on an end of the storage (whole row if j / k sit on one)
+    const bool row_ok = j > 0 && j < g.ny - 1 && (!g.is3d || (k > 0 && k < g.nz - 1));
+    int r = -1;
+    if (row_ok && i > 0 && i < g.nx - 1 && (flag_at(row, i) & kFluid)) {
+      r = 0;
+      for (int d = 1; d <= kClearMax; d++) {
+        if (i - d < 1 || i + d > g.nx - 2 || !(flag_at(row, i - d) & kFluid) || !(flag_at(row, i + d) & kFluid)) break;
+        r = d;
+      }
     }
+    out[t] = (unsigned char)(r < 0 ? 255 : r);      // 255 marks an unusable cell for the next pass
   }
-  // 255 marks a non-fluid cell for the next pass (clearance 0 is "fluid, no clear neighbourhood")
-  out[b * g.n + cell(g, k, j, i)] = (unsigned char)(r < 0 ? 255 : r);
 }
-// AXIS 1: y, 2: z.  `in` holds the previous pass (255 = non-fluid), `out` the combined radius; the last
-// pass writes 0 for non-fluid cells.
+// AXIS 1: y, 2: z.  `in` holds the previous pass (255 = unusable cell), `out` the combined radius r of the
+// all-usable box; the last pass writes the distance r + 1, and 0 for unusable cells.
 template <int AXIS, bool LAST>
 __global__ void k_clear_axis(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, Geo g,
                              const int* __restrict__ gate) {
-  int b, k, j, i;
   if (gate && *gate == 0) return;
-  if (!thread_cell(g, b, k, j, i)) return;
-  const int c = b * g.n + cell(g, k, j, i);
-  const int stride = AXIS == 1 ? g.nx : g.nx * g.ny;
-  const int pos = AXIS == 1 ? j : k, ext = AXIS == 1 ? g.ny : g.nz;
-  const int self = in[c];
-  int r;
-  if (self == 255) {
-    r = LAST ? 0 : 255;
-  } else {
-    r = 0;
-    int m = self;
-    for (int d = 1; d <= kClearMax; d++) {
-      if (pos - d < 0 || pos + d >= ext) break;
-      const int a = in[c - d * stride], bb = in[c + d * stride];
-      if (a == 255 || bb == 255) break;
-      m = min(m, min(a, bb));
-      if (m < d) break;
-      r = d;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;; t += (long long)gridDim.x * blockDim.x) {
+    int b, k, j, i;
+    if (!clear_cell(g, t, b, k, j, i)) return;
+    const int stride = AXIS == 1 ? g.nx : g.nx * g.ny;
+    const int pos = AXIS == 1 ? j : k, ext = AXIS == 1 ? g.ny : g.nz;
+    const int self = in[t];
+    int r;
+    if (self == 255) {
+      r = LAST ? 0 : 255;
+    } else {
+      r = 0;
+      int m = self;
+      for (int d = 1; d <= kClearMax; d++) {
+        if (pos - d < 0 || pos + d >= ext) break;
+        const int a = in[t - d * stride], bb = in[t + d * stride];
+        if (a == 255 || bb == 255) break;
+        m = min(m, min(a, bb));
+        if (m < d) break;
+        r = d;
+      }
+      if (LAST) r += 1;
     }
+    out[t] = (unsigned char)r;
   }
-  out[c] = (unsigned char)r;
 }
 template <typename FT>
-int launch_clearance(const FT* flags, unsigned char* clear, unsigned char* tmp, const Geo& gin, const int* gate,
+int launch_clearance(const FT* flags, unsigned char* clear, unsigned char* tmp, const Geo& g, const int* gate,
                      cudaStream_t st) {
-  Geo g = gin;
-  g.zlo = 0; g.zhi = g.nz;                 // the whole local storage, whatever range the operator computes
-  dim3 grid, block;
-  launch_dims(g, grid, block);
+  const long long total = g.n * g.nb;
+  const int block = 256;
+  const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 8);
   if (g.is3d) {                            // (a 3-D grid with fewer than 3 planes gets clearance 0)
     k_clear_x<FT><<<grid, block, 0, st>>>(flags, clear, g, gate);
     k_clear_axis<1, false><<<grid, block, 0, st>>>(clear, tmp, g, gate);

@@ -175,4 +175,7 @@ def simulate_fused(conf, mconf, batch, model=None):
     c = tfluids._ctx_for(p)
     st = make_state(batch)
     mc = make_mconf(mconf)
+    if model is not None:
+        # one source for the input-scale threshold: the model's (what `simulate` uses through model.forward)
+        mc.normalize_input_threshold = float(model.threshold)
     c.check(c.lib.tfl_simulate_step(c.h, C.byref(st), C.byref(mc), model.h if model is not None else None))

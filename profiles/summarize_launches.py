@@ -1,27 +1,26 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel name."""
+"""Mean device time per kernel of an `ncu --metrics gpu__time_duration.sum --csv` launch list."""
 import collections
 import csv
 import sys
 
 
 def main(path):
-    with open(path) as f:
-        lines = [l for l in f if not l.startswith("==")]
-    tot = collections.defaultdict(lambda: [0, 0.0])
-    for row in csv.DictReader(lines):
-        try:
-            v = float(row["Metric Value"].replace(",", ""))
-        except (KeyError, ValueError):
+    hdr = None
+    agg = collections.OrderedDict()
+    for r in csv.reader(open(path)):
+        if hdr is None:
+            if "Kernel Name" in r:
+                hdr = r
+                ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
             continue
-        unit = row["Metric Unit"]
-        v = v / 1000 if unit == "ns" else (v * 1000 if unit == "ms" else v)
-        tot[row["Kernel Name"]][0] += 1
-        tot[row["Kernel Name"]][1] += v
-    total = sum(t for _, t in tot.values())
-    for n, (c, t) in sorted(tot.items(), key=lambda x: -x[1][1]):
-        print("%-64s n=%3d total=%9.1f us avg=%8.1f us  %4.1f%%" % (n[:64], c, t, t / c, 100 * t / total))
+        if len(r) > vi and r[0].isdigit():
+            agg.setdefault(r[ki][:78], []).append(float(r[vi].replace(",", "")))
+    tot = 0.0
+    for k, v in agg.items():
+        print("%-80s n=%-3d mean=%8.1f us" % (k, len(v), sum(v) / len(v) / 1000))
+    return 0
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    sys.exit(main(sys.argv[1]))

@@ -261,3 +261,71 @@ def test_full_size_properties():
     tfluids.setWallBcsForward(U2, flags)
     assert torch.equal(U, U2)
     assert tfluids.context().trace_faults() == 0
+
+
+def test_fused_step_with_non_idempotent_density_bc():
+    """setConstVals runs three times per step (lib/simulate.lua:202, :252, :321).  With an additive density
+    BC (invMask = 1 where bc != 0) the three applications do not collapse into one: the fused step must still
+    equal the operator sequence."""
+    from fluidnet_b200 import simulate
+    from gpu_backend import make_gpu_model
+    n = 32
+    batch = make_batch(n, True)
+    rs = np.random.RandomState(5)
+    batch["densityBC"] = (rs.rand(*batch["density"].shape) < 0.1).astype(np.float32) * np.float32(0.25)
+    batch["densityBCInvMask"] = np.where(rs.rand(*batch["density"].shape) < 0.5, 1.0, 0.5).astype(np.float32)
+    gm = make_gpu_model(synth.make_model(True))
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=0.5,
+                                 vorticityConfinementAmp=3.0, simMethod="convnet")
+    a, b = to_gpu(batch), to_gpu(batch)
+    for _ in range(2):
+        simulate.simulate(None, mconf, a, gm)
+        simulate.simulate_fused(None, mconf, b, gm)
+    assert bits_equal(a["density"].cpu().numpy(), b["density"].cpu().numpy())
+    for k in ("UDiv", "pDiv"):
+        close(a[k].cpu().numpy(), b[k].cpu().numpy(), 1e-6, k)
+
+
+def test_fused_step_on_unaligned_views():
+    """Caller-owned grids that are contiguous but only 4-byte aligned (a view with an odd storage offset):
+    the 16-byte kernels must step aside, results equal the aligned run bit for bit."""
+    from fluidnet_b200 import simulate
+    from gpu_backend import make_gpu_model
+    n = 32
+    batch = make_batch(n, True)
+    gm = make_gpu_model(synth.make_model(True))
+    mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=0.5,
+                                 vorticityConfinementAmp=3.0, simMethod="convnet")
+    a = to_gpu(batch)
+    b = {}
+    for k, v in to_gpu(batch).items():
+        flat = torch.empty(v.numel() + 1, device="cuda", dtype=v.dtype)
+        view = flat[1:].view(v.shape)
+        view.copy_(v)
+        assert view.data_ptr() % 16 == 4 and view.is_contiguous()
+        b[k] = view
+    simulate.simulate_fused(None, mconf, a, gm)
+    simulate.simulate_fused(None, mconf, b, gm)
+    torch.cuda.synchronize()
+    assert bits_equal(a["density"].cpu().numpy(), b["density"].cpu().numpy())
+    for k in ("UDiv", "pDiv"):
+        close(a[k].cpu().numpy(), b[k].cpu().numpy(), 1e-6, k)
+
+
+def test_operators_on_a_non_current_device(orc):
+    """Contexts select their own device: tensors on cuda:1 while the current device is cuda:0 (needs 2 GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from fluidnet_b200 import tfluids
+    c = make_batch(20, True, plume=False)
+    want = orc.advectVel(0.1, c["UDiv"], c["flags"], "maccormackOurs", 0.6)
+    torch.cuda.set_device(0)
+    U = torch.from_numpy(c["UDiv"]).to("cuda:1")
+    fl = torch.from_numpy(c["flags"]).to("cuda:1")
+    out = torch.empty_like(U)
+    tfluids.advectVel(0.1, U, fl, "maccormackOurs", out, 0.6)
+    assert torch.cuda.current_device() == 0
+    assert bits_equal(out.cpu().numpy(), want)
+    div = torch.empty_like(fl)
+    tfluids.velocityDivergenceForward(U, fl, div)
+    assert bits_equal(div.cpu().numpy(), orc.velocityDivergenceForward(c["UDiv"], c["flags"]))
