@@ -52,6 +52,16 @@ struct tfl_ctx {
     int nb = 0, nz = 0, ny = 0, nx = 0;
     int* changed = nullptr;                 // device word
   } fcache;
+  // advectVel over shared-memory tiles (tfl_advect_tile.cu): the kernel reports the longest trace of a call
+  // into a device word that is copied, asynchronously, into a pinned host word; the NEXT calls pick the tile
+  // halo from it (stale by a step or two -- it only selects a code path, never a result).
+  struct {
+    unsigned int* dev = nullptr;
+    unsigned int* host = nullptr;           // pinned
+    int mode = -1;                          // -1 automatic, 0 two-kernel version, 1 / 2 forced halo
+    int variant = 0;                        // tile shape (tuning)
+    int calls_since_probe = 0;
+  } tile;
 };
 
 struct tfl_cnn {
@@ -235,6 +245,39 @@ int prepare_flags(tfl_ctx* ctx, const float* flags, const Geo& g, unsigned char*
   return 0;
 }
 
+// advectVel('maccormackOurs') dispatch: the tile kernel when the grid qualifies and the traces of the recent
+// calls fit its halo, the two-kernel version otherwise.  Returns the launch count, < 0 for a bad method.
+template <typename FT>
+int advect_vel_dispatch(tfl_ctx* ctx, float dt, const float* U, const FT* flags, const unsigned char* fl8,
+                        const unsigned char* clear, int method, float strength, float* dst, float* fwd, const Geo& g,
+                        const Geo& gf, cudaStream_t st) {
+  const bool ours = method == TFL_ADVECT_MACCORMACK_OURS || method == TFL_ADVECT_RK2_OURS || method == TFL_ADVECT_RK3_OURS;
+  auto& tl = ctx->tile;
+  if (ours && fl8 && clear && tl.mode != 0) {
+    if (!tl.dev) {
+      void* p = nullptr;
+      if (cudaMalloc(&p, sizeof(unsigned int)) == cudaSuccess) tl.dev = (unsigned int*)p;
+      if (cudaHostAlloc(&p, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) { tl.host = (unsigned int*)p; *tl.host = 0; }
+    }
+    int hf = tl.mode;
+    if (hf < 0) {
+      float longest = 0.0f;
+      if (tl.host) { const unsigned int bits = *(volatile unsigned int*)tl.host; memcpy(&longest, &bits, 4); }
+      hf = longest < 0.45f ? 1 : (longest < 1.4f ? 2 : 0);
+      // beyond the wide halo the two-kernel version is faster; look again every 16th call
+      if (hf == 0 && ++tl.calls_since_probe >= 16) { hf = 2; tl.calls_since_probe = 0; }
+    }
+    if (hf > 0 && tl.dev && tl.host) {
+      cudaMemsetAsync(tl.dev, 0, sizeof(unsigned int), st);
+      if (launch_advect_vel_tile(dt, U, fl8, clear, strength, dst, g, hf, tl.variant, tl.dev, st)) {
+        cudaMemcpyAsync(tl.host, tl.dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+        return 1;
+      }
+    }
+  }
+  return launch_advect_vel(dt, U, flags, clear, method, strength, dst, fwd, g, gf, st);
+}
+
 float get_dx(const Geo& g) {     // third_party/grid.cc:37-40 on the GLOBAL grid
   int m = g.nx > g.ny ? g.nx : g.ny;
   if (g.gnz > m) m = g.gnz;
@@ -298,6 +341,8 @@ void tfl_destroy(tfl_ctx* ctx) {
   pcg_release(ctx->pcg);
   if (ctx->fcache.bytes) cudaFree(ctx->fcache.bytes);
   if (ctx->fcache.changed) cudaFree(ctx->fcache.changed);
+  if (ctx->tile.dev) cudaFree(ctx->tile.dev);
+  if (ctx->tile.host) cudaFreeHost(ctx->tile.host);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -566,8 +611,8 @@ int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* fl
   widen_for_forward_pass(ctx, g, &gf);
   const bool traced = method != TFL_ADVECT_EULER && method != TFL_ADVECT_MACCORMACK;
   if (traced && prepare_flags(ctx, flags->data, g, &fl8, &clear)) return 1;
-  const int nl = launch_advect_vel(dt, U->data, flags->data, traced ? clear : nullptr, method, strength, dst, fwd, g,
-                                   gf, ctx->stream);
+  const int nl = advect_vel_dispatch(ctx, dt, U->data, flags->data, fl8, traced ? clear : nullptr, method, strength, dst,
+                                     fwd, g, gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectVel: bad method");
   ctx->launches += nl;
   if (check_launch(ctx, "advectVel")) return 1;
@@ -916,6 +961,14 @@ int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
 }
 int tfl_cnn_get_mode(const tfl_cnn* m) { return m ? m->mode : -1; }
 // Undocumented debugging hook: 0 forces the shared-memory-operand kernel in 3xTF32 mode.
+// mode: -1 automatic, 0 two-kernel advectVel, 1 / 2 tile kernel with that halo; variant: tile shape.
+int tfl_debug_advect_tile(tfl_ctx* ctx, int mode, int variant) {
+  if (!ctx) return 1;
+  ctx->tile.mode = mode;
+  ctx->tile.variant = variant;
+  return 0;
+}
+
 int tfl_debug_cnn_use_ts(tfl_cnn* m, int on) { if (m) m->use_ts = on; return 0; }
 // Undocumented debugging hook (not in tfl.h): per-CTA phase timestamps of the tensor-core conv.
 int tfl_debug_conv_timestamps(void* dev_buf) { conv_tc_set_debug((long long*)dev_buf); return 0; }
@@ -1200,8 +1253,8 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
   }
   {
-    const int nl = launch_advect_vel(mc->dt, s->U.data, fl8, clear, mc->advection_method,
-                                     mc->maccormack_strength, tmp_u, fwd_u, g, g, st);
+    const int nl = advect_vel_dispatch(ctx, mc->dt, s->U.data, fl8, fl8, clear, mc->advection_method,
+                                       mc->maccormack_strength, tmp_u, fwd_u, g, g, st);
     if (nl < 0) return fail(ctx, "advectVel: bad method");
     ctx->launches += nl;
   }

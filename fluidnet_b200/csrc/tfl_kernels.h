@@ -34,6 +34,13 @@ int launch_advect_scalar(float dt, const float* s, const float* U, const FT* fla
 template <typename FT>
 int launch_advect_vel(float dt, const float* U, const FT* flags, const unsigned char* clear, int method,
                       float strength, float* dst, float* fwd, const Geo& g, const Geo& g_fwd, cudaStream_t st);
+// ---- tfl_advect_tile.cu (-fmad=false): maccormackOurs advectVel as one kernel over shared-memory tiles ----
+// hf: halo of the forward field in cells (1: traces < ~0.5 cell are served from the tile, 2: < ~1.5; longer ones
+// take the general code).  longest: optional device word, atomicMax of the longest trace (float bits).
+// Returns false when the grid does not qualify (2-D, batch, slab, nx % 4 != 0): run launch_advect_vel then.
+bool launch_advect_vel_tile(float dt, const float* U, const unsigned char* flags, const unsigned char* clear,
+                            float strength, float* dst, const Geo& g, int hf, int variant, unsigned int* longest,
+                            cudaStream_t st);
 // Clearance of every cell of the local storage (advection fast path, tfl_device.cuh); tmp: scratch of the
 // same size; gate: optional device word, the kernels do nothing when it is 0.  Returns the launch count.
 template <typename FT>
