@@ -245,6 +245,19 @@ int prepare_flags(tfl_ctx* ctx, const float* flags, const Geo& g, unsigned char*
   return 0;
 }
 
+// Halo of the advection tile kernels for this call (0: use the per-pass kernels), from the longest trace the
+// velocity kernel reported on earlier calls.
+int tile_halo_choice(tfl_ctx* ctx, bool probe) {
+  auto& tl = ctx->tile;
+  if (tl.mode >= 0) return tl.mode;
+  float longest = 0.0f;
+  if (tl.host) { const unsigned int bits = *(volatile unsigned int*)tl.host; memcpy(&longest, &bits, 4); }
+  int hf = longest < 0.45f ? 1 : (longest < 1.4f ? 2 : 0);
+  // beyond the wide halo the per-pass kernels are faster; the velocity kernel looks again every 16th call
+  if (hf == 0 && probe && ++tl.calls_since_probe >= 16) { hf = 2; tl.calls_since_probe = 0; }
+  return hf;
+}
+
 // advectVel('maccormackOurs') dispatch: the tile kernel when the grid qualifies and the traces of the recent
 // calls fit its halo, the two-kernel version otherwise.  Returns the launch count, < 0 for a bad method.
 template <typename FT>
@@ -259,14 +272,7 @@ int advect_vel_dispatch(tfl_ctx* ctx, float dt, const float* U, const FT* flags,
       if (cudaMalloc(&p, sizeof(unsigned int)) == cudaSuccess) tl.dev = (unsigned int*)p;
       if (cudaHostAlloc(&p, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) { tl.host = (unsigned int*)p; *tl.host = 0; }
     }
-    int hf = tl.mode;
-    if (hf < 0) {
-      float longest = 0.0f;
-      if (tl.host) { const unsigned int bits = *(volatile unsigned int*)tl.host; memcpy(&longest, &bits, 4); }
-      hf = longest < 0.45f ? 1 : (longest < 1.4f ? 2 : 0);
-      // beyond the wide halo the two-kernel version is faster; look again every 16th call
-      if (hf == 0 && ++tl.calls_since_probe >= 16) { hf = 2; tl.calls_since_probe = 0; }
-    }
+    const int hf = tile_halo_choice(ctx, true);
     if (hf > 0 && tl.dev && tl.host) {
       cudaMemsetAsync(tl.dev, 0, sizeof(unsigned int), st);
       if (launch_advect_vel_tile(dt, U, fl8, clear, strength, dst, g, hf, tl.variant, tl.dev, st)) {
@@ -276,6 +282,18 @@ int advect_vel_dispatch(tfl_ctx* ctx, float dt, const float* U, const FT* flags,
     }
   }
   return launch_advect_vel(dt, U, flags, clear, method, strength, dst, fwd, g, gf, st);
+}
+
+template <typename FT>
+int advect_scalar_dispatch(tfl_ctx* ctx, float dt, const float* s, const float* U, const FT* flags,
+                           const unsigned char* fl8, const unsigned char* clear, int method, int outside, float strength,
+                           float* dst, float* fwd, float* fwd_pos, const Geo& g, const Geo& gf, cudaStream_t st) {
+  if (method == TFL_ADVECT_MACCORMACK_OURS && fl8 && clear && ctx->tile.mode != 0) {
+    const int hf = tile_halo_choice(ctx, false);
+    if (hf > 0 && launch_advect_scalar_tile(dt, s, U, fl8, clear, outside, strength, dst, g, hf, ctx->tile.variant, st))
+      return 1;
+  }
+  return launch_advect_scalar(dt, s, U, flags, clear, method, outside, strength, dst, fwd, fwd_pos, g, gf, st);
 }
 
 float get_dx(const Geo& g) {     // third_party/grid.cc:37-40 on the GLOBAL grid
@@ -575,8 +593,8 @@ int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid*
   widen_for_forward_pass(ctx, g, &gf);
   const bool traced = method == TFL_ADVECT_EULER_OURS || method == TFL_ADVECT_MACCORMACK_OURS;
   if (traced && prepare_flags(ctx, flags->data, g, &fl8, &clear)) return 1;
-  const int nl = launch_advect_scalar(dt, s->data, U->data, flags->data, traced ? clear : nullptr, method,
-                                      sample_outside_fluid, strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
+  const int nl = advect_scalar_dispatch(ctx, dt, s->data, U->data, flags->data, fl8, traced ? clear : nullptr, method,
+                                        sample_outside_fluid, strength, dst, fwd, fwd_pos, g, gf, ctx->stream);
   if (nl < 0) return fail(ctx, "advectScalar: bad method");
   ctx->launches += nl;
   if (check_launch(ctx, "advectScalar")) return 1;
@@ -1246,8 +1264,8 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
     if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_d_in, 0));
-    const int nl = launch_advect_scalar(mc->dt, s->density.data, s->U.data, fl8, clear, mc->advection_method, 0,
-                                        mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
+    const int nl = advect_scalar_dispatch(ctx, mc->dt, s->density.data, s->U.data, fl8, fl8, clear, mc->advection_method,
+                                          0, mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
     if (nl < 0) return fail(ctx, "advectScalar: bad method");
     ctx->launches += nl;
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));

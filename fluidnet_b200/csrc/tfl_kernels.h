@@ -41,6 +41,10 @@ int launch_advect_vel(float dt, const float* U, const FT* flags, const unsigned 
 bool launch_advect_vel_tile(float dt, const float* U, const unsigned char* flags, const unsigned char* clear,
                             float strength, float* dst, const Geo& g, int hf, int variant, unsigned int* longest,
                             cudaStream_t st);
+// advectScalar('maccormackOurs') on the same tiles.
+bool launch_advect_scalar_tile(float dt, const float* src, const float* U, const unsigned char* flags,
+                               const unsigned char* clear, int outside, float strength, float* dst, const Geo& g, int hf,
+                               int variant, cudaStream_t st);
 // Clearance of every cell of the local storage (advection fast path, tfl_device.cuh); tmp: scratch of the
 // same size; gate: optional device word, the kernels do nothing when it is 0.  Returns the launch count.
 template <typename FT>

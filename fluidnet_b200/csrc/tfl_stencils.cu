@@ -385,75 +385,7 @@ __global__ void k_advect_scalar_pass2_ours(const float* __restrict__ s, const fl
   if (!border) {
     const float* pp = fwd_pos + (long long)b * g.nc * g.n + c;
     const float px = __ldg(pp), py = __ldg(pp + g.n), pz = g.is3d ? __ldg(pp + 2 * g.n) : 0.0f;
-    const int i0 = clamp_i((int)px, 0, g.nx - 1), j0 = clamp_i((int)py, 0, g.ny - 1);
-    const int k0 = g.is3d ? clamp_i((int)pz, 0, g.gnz - 1) : 0;
-    float lo = INFINITY, hi = -INFINITY;
-    int found = 0;
-    const int kl0 = k0 - g.zoff;
-    const bool interior = i0 >= 1 && i0 <= g.nx - 2 && j0 >= 1 && j0 <= g.ny - 2 &&
-                          (!g.is3d || (k0 >= 1 && k0 <= g.gnz - 2 && kl0 >= 1 && kl0 <= g.nz - 2));
-    if (interior) {
-      // Same cells in the same order as the general loop below, without its bounds tests: the
-      // 27 (9 in 2-D) neighbours sit at fixed offsets from the centre.
-      const int ctr = cell(g, g.is3d ? kl0 : 0, j0, i0);
-      const int sy = g.nx, sz = g.nx * g.ny;
-      // clearance >= 2 at the centre of the neighbourhood: all of it is fluid, no flag is read
-      const bool all_fluid = outside || (cl && __ldg(cl + ctr) > 1);
-      if (all_fluid) {
-        found = 1;
-#pragma unroll
-        for (int dz = -1; dz <= 1; dz++) {
-          if (!g.is3d && dz != 0) continue;
-#pragma unroll
-          for (int dy = -1; dy <= 1; dy++) {
-            const float* srow = sb + (ctr + dz * sz + dy * sy);
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-              const float t = __ldg(srow + dx);
-              lo = (t < lo) ? t : lo;
-              hi = (t > hi) ? t : hi;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-      for (int dz = -1; dz <= 1; dz++) {
-        if (!g.is3d && dz != 0) continue;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-          // one pointer pair per row: the three cells of a row are immediate offsets -1, 0, +1
-          const float* srow = sb + (ctr + dz * sz + dy * sy);
-          const FT* frow = fl + (ctr + dz * sz + dy * sy);
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            const float t = __ldg(srow + dx);
-            const bool use = (flag_at(frow, dx) & kFluid);
-            lo = (use && t < lo) ? t : lo;
-            hi = (use && t > hi) ? t : hi;
-            found |= use ? 1 : 0;
-          }
-        }
-      }
-      }
-    } else {
-    for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
-      if (kk < 0 || kk >= g.gnz) continue;
-      const int kl = local_z(g, kk);
-      for (int jj = j0 - 1; jj <= j0 + 1; jj++) {
-        if (jj < 0 || jj >= g.ny) continue;
-        for (int ii = i0 - 1; ii <= i0 + 1; ii++) {
-          if (ii < 0 || ii >= g.nx) continue;
-          if (outside || (flag_i(fl, g, kl, jj, ii) & kFluid)) {
-            const float t = __ldg(sb + cell(g, kl, jj, ii));
-            if (t < lo) lo = t;
-            if (t > hi) hi = t;
-            found++;
-          }
-        }
-      }
-    }
-    }
-    v = (found < 1) ? fw : clamp_f(v, lo, hi);
+    v = clamp_scalar_ours(sb, fl, cl, g, v, fw, px, py, pz, outside != 0);
   }
   dst[b * g.n + c] = v;
 }

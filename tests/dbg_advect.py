@@ -56,6 +56,15 @@ for mode, variant in [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (2, 0), (2
     same = torch.equal(ref.view(torch.int32), Ud.view(torch.int32))
     print("advectVel mode %d variant %d: %.1f us  %s" % (mode, variant, t, "== first" if same else "DIFFERS"), flush=True)
 ctx.lib.tfl_debug_advect_tile(ctx.h, -1, 0)
+ref = None
+for mode, variant in [(0, 0), (1, 0), (1, 1), (2, 0)]:
+    ctx.lib.tfl_debug_advect_tile(ctx.h, mode, variant)
+    t = timed(lambda: tfluids.advectScalar(0.1, rho, U, fl, "maccormackOurs", rd, False, 0.6))
+    if ref is None:
+        ref = rd.clone()
+    same = torch.equal(ref.view(torch.int32), rd.view(torch.int32))
+    print("advectScalar mode %d variant %d: %.1f us  %s" % (mode, variant, t, "== first" if same else "DIFFERS"), flush=True)
+ctx.lib.tfl_debug_advect_tile(ctx.h, -1, 0)
 t_v = timed(lambda: tfluids.advectVel(0.1, U, fl, "maccormackOurs", Ud, 0.6))
 t_s = timed(lambda: tfluids.advectScalar(0.1, rho, U, fl, "maccormackOurs", rd, False, 0.6))
 print("advectVel %.1f us   advectScalar %.1f us   (%d^3, %s velocity, L2 flushed)" % (t_v, t_s, n, velocity), flush=True)

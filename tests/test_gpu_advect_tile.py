@@ -51,6 +51,31 @@ def test_tile_modes_match_oracle(orc, gpu, dims, geom, exotic, amp):
     assert gpu.trace_faults() == 0
 
 
+@pytest.mark.parametrize("dims,geom,exotic", GRIDS, ids=["40x24x20_geom", "36x20x12_exotic", "64x16x5_empty"])
+@pytest.mark.parametrize("amp", [2.0, 8.0, 25.0])
+def test_scalar_tile_modes_match_oracle(orc, gpu, dims, geom, exotic, amp):
+    """advectScalar('maccormackOurs') on the tiles, both sampleOutsideFluid settings, every dispatcher choice."""
+    nx, ny, nz = dims
+    flags = synth.make_flags(nx, ny, nz, True, nb=1, geometry=geom, exotic=exotic)
+    U = synth.make_velocity(flags, True, amp=amp)
+    orc.setWallBcsForward(U, flags)
+    rho = synth.make_density(flags)
+    rho[np.random.RandomState(3).rand(*rho.shape) < 0.3] = 0.0          # zero bounds in the clamp
+    try:
+        for outside in (False, True):
+            want = orc.advectScalar(0.1, rho, U, flags, "maccormackOurs", outside, 0.6)
+            for mode, variant in [(0, 0), (1, 0), (1, 1), (2, 0), (-1, 0)]:
+                set_tile(mode, variant)
+                got = gpu.advectScalar(0.1, rho, U, flags, "maccormackOurs", outside, 0.6)
+                assert bits_equal(got, want), "outside %s mode %d variant %d: %s" % (outside, mode, variant,
+                                                                                      describe_diff(got, want))
+            got = gpu.advectScalar(0.1, rho, U, flags, "maccormackOurs", outside, 0.6, in_place=True)
+            assert bits_equal(got, want), "in place: " + describe_diff(got, want)
+    finally:
+        set_tile(-1, 0)
+    assert gpu.trace_faults() == 0
+
+
 def test_zero_bounds_keep_their_sign(orc, gpu):
     """The clamp's min / max run on FMNMX with an exact re-evaluation when a bound is +-0: fields with large
     regions of +0 and -0 velocities must still match the reference's compare-and-keep bit for bit."""
