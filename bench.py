@@ -205,56 +205,79 @@ def run_reference(args):
     return 0
 
 
-def run_slab(args, world, rank, local):
-    """BASELINE config 5: one domain split in z across the ranks (fluidnet_b200.slab)."""
+def measure_slab(n, steps, warmup, world, rank, local):
+    """BASELINE config 5: ONE n^3 domain split in z across the ranks, stepped by tfl_slab_sim_step (the library
+    owns the NCCL communicator; neighbour ncclSend / ncclRecv straight on the field arrays).  Strong scaling.
+    Returns the record (rank 0) or None."""
     import torch
     import torch.distributed as dist
-    from fluidnet_b200.slab import SlabSimulator
-    n = args.grid
+    from fluidnet_b200.slab import NativeSlabSimulator
     batch_np, mconf, mnp = make_problem(n)
     tb = {k: torch.from_numpy(v) for k, v in batch_np.items()}
-    sim = SlabSimulator(tb, mconf, mnp["layers"], torch.device("cuda", local), rank, world)
+    sim = NativeSlabSimulator(tb, mconf, mnp["layers"], torch.device("cuda", local), rank, world)
     del tb
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(warmup, 3)
+    for _ in range(warmup):
         sim.step()
     sim.check()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sim.ctx.launch_count()
-    e0.record()
-    for _ in range(args.steps):
+    e0.record(stream)
+    for _ in range(steps):
         sim.step()
-    e1.record()
+    e1.record(stream)
     torch.cuda.synchronize()
     launches = sim.ctx.launch_count() - l0
     if world > 1:
         dist.barrier()
-    if rank == 0:
-        sampler.stop_flag.set()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ex_ms, ex_bytes = sim.exchange_stats()
+    ex = torch.tensor(ex_ms, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ex, op=dist.ReduceOp.MAX)
     sim.check()
+    sim.close()
+    if rank != 0:
+        return None
+    ms = t.item() / steps
+    ex = [float(v) for v in ex.tolist()]
+    names = ["U+density, %d planes (before the advection)" % (2 * 2 + 2), "U+density, 4 planes (before the forces)",
+             "U+p, 5 planes (before the projection)"]
+    limiting = names[max(range(3), key=lambda i: ex[i])] if world > 1 else None
+    return {"metric": "sim steps/sec on ONE %d^3 MAC grid (CNN proj), z-slab decomposed" % n, "value": 1000.0 / ms,
+            "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "scaling": "strong", "grid": [n, n, n],
+            "parallelism": "z-slab x%d; per step 3 neighbour halo exchanges (ncclSend/ncclRecv grouped per phase, "
+                           "no packing) + one 2-double ncclAllReduce, all issued by libtfl (tfl_slab_sim_step)" % world,
+            "halo_bytes_sent_per_rank_step": int(sum(ex_bytes)),
+            "exchange_ms_last_step_max_over_ranks": {"halo_advect": ex[0], "halo_forces": ex[1],
+                                                     "halo_projection": ex[2], "allreduce": ex[3]},
+            "limiting_exchange": limiting,
+            "l2": "working set %d MB per rank; no flush between steps" % (60 * (n / 128.0) ** 3 / world),
+            "gpu_launches": int(launches)}
+
+
+def run_slab(args, world, rank, local):
+    """--mode slab: only the z-slab measurement, as its own JSON line."""
+    import torch.distributed as dist
+    sampler = ClockSampler(local)
     if rank == 0:
-        ms = t.item() / args.steps
-        halo_bytes = (2 * (4 * 6 + 4 * 4 + 4 * 5)) * n * n * 4 if world > 1 else 0
-        print(json.dumps({
-            "metric": "sim steps/sec on %d^3 MAC grid (CNN proj), one domain z-slab decomposed" % n,
-            "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ONE 3D %d^3 MAC grid split in z over %d GPU(s): maccormackOurs advection + plume "
-                                   "BCs + buoyancy + vorticity confinement + CNN projection; 3 neighbour halo "
-                                   "exchanges (widths 6/4/5 planes) + one 2-double all-reduce per step" % (n, world),
-                       "grid": [n, n, n], "parallelism": "z-slab x%d, NCCL send/recv halos" % world,
-                       "halo_bytes_per_rank_step": halo_bytes,
-                       "l2": "working set %d MB per rank > L2 at 256^3; no flush between steps" % (60 * (n / 128.0) ** 3 / world)},
-            "gpu_launches": int(launches), "clocks": sampler.summary()}))
+        sampler.start()
+    rec = measure_slab(args.grid, args.steps, args.warmup, world, rank, local)
+    if rank == 0:
+        sampler.stop_flag.set()
+        rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": "ONE 3D %d^3 MAC grid split in z over %d GPU(s): maccormackOurs advection + "
+                                           "plume BCs + buoyancy + vorticity confinement + CNN projection" % (args.grid, world),
+                               "grid": rec["grid"], "parallelism": rec["parallelism"]},
+                    "clocks": sampler.summary()})
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -268,6 +291,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--grid", type=int, default=N_GRID)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="skip the 256^3 z-slab (BASELINE config 5) sub-record")
+    ap.add_argument("--slab-grid", type=int, default=256)
     ap.add_argument("--no-extra", action="store_true", help="skip the Jacobi / PCG side measurements (kernel experiments)")
     ap.add_argument("--mode", default="grids", choices=["grids", "slab"],
                     help="grids: one independent --grid^3 domain per GPU (weak scaling, the default and the "
@@ -449,6 +474,13 @@ def main():
                     del Uj
                 del fl, dv, pj
 
+    # ---- BASELINE config 5 beside the headline: ONE 256^3 domain in z-slabs over the same ranks (strong scaling)
+    slab = None
+    if not args.no_slab:
+        del gb
+        torch.cuda.empty_cache()
+        slab = measure_slab(args.slab_grid, max(3, min(args.steps, 10)), 3, world, rank, local)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -497,6 +529,7 @@ def main():
                      "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms,
                      "limiter": "instruction issue (ncu tables under profiles/)"},
         "roofline_extra": extra,
+        "slab": slab,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }

@@ -43,7 +43,11 @@ SYMBOLS = [
     "tfl_velocity_update_backward", "tfl_volumetric_up_sampling_nearest_backward", "tfl_empty_domain", "tfl_flags_to_occupancy", "tfl_apply_bc",
     "tfl_clamp", "tfl_cnn_create", "tfl_cnn_create_graph", "tfl_cnn_destroy", "tfl_cnn_set_mode", "tfl_cnn_get_mode", "tfl_cnn_project", "tfl_simulate_step",
     "tfl_host_sim_create", "tfl_host_sim_destroy", "tfl_host_sim_step",
+    "tfl_comm_unique_id", "tfl_comm_init", "tfl_comm_destroy", "tfl_slab_sim_create", "tfl_slab_sim_destroy",
+    "tfl_slab_sim_layout", "tfl_slab_sim_upload", "tfl_slab_sim_download", "tfl_slab_sim_step",
+    "tfl_slab_sim_exchange_stats",
 ]
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -119,6 +123,17 @@ def load():
     lib.tfl_host_sim_destroy.argtypes = [C.c_void_p, C.c_void_p]
     lib.tfl_host_sim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(MConf), C.c_void_p]
+    lib.tfl_comm_unique_id.argtypes = [C.c_void_p, C.c_char_p]
+    lib.tfl_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
+    lib.tfl_comm_destroy.argtypes = [C.c_void_p]
+    lib.tfl_slab_sim_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.tfl_slab_sim_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tfl_slab_sim_layout.argtypes = [C.c_void_p, C.POINTER(State), C.POINTER(C.c_int32)]
+    lib.tfl_slab_sim_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tfl_slab_sim_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tfl_slab_sim_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MConf), C.c_void_p]
+    lib.tfl_slab_sim_exchange_stats.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.tfl_alloc_host.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.tfl_free_host.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib

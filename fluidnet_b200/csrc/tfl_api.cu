@@ -3,6 +3,8 @@
 // whole-step entry points that enqueue the kernels of tfl_stencils.cu, tfl_model_stages.cu
 // and tfl_cnn*.cu on the context's stream.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: libnccl is loaded on demand (dlopen), see NcclApi
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -62,6 +64,9 @@ struct tfl_ctx {
     int variant = 0;                        // tile shape (tuning)
     int calls_since_probe = 0;
   } tile;
+  // z-slab decomposition over several GPUs (tfl_comm_init / tfl_slab_sim_*): the communicator lives here
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
 
 struct tfl_cnn {
@@ -361,6 +366,7 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->fcache.changed) cudaFree(ctx->fcache.changed);
   if (ctx->tile.dev) cudaFree(ctx->tile.dev);
   if (ctx->tile.host) cudaFreeHost(ctx->tile.host);
+  tfl_comm_destroy(ctx);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -1484,6 +1490,332 @@ int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float*
     TFL_CUDA(ctx, cudaMemcpyAsync(density, s.density.data, hs->cells * 4, cudaMemcpyDeviceToHost, st));
   if (density_sent) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_d_out, 0));
   TFL_CUDA(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// One domain split into z-slabs over the GPUs of a node.  The reference is
+// single-GPU; this is the multi-GPU form of the same step: rank r owns the planes [z0, z1) of every
+// field plus `halo` ghost planes per interior side, every kernel works in GLOBAL coordinates
+// (tfl_set_slab), and ghost planes are refreshed by neighbour ncclSend / ncclRecv pairs straight
+// from and into the field arrays (the planes of one channel are contiguous: nothing is packed),
+// grouped into one NCCL operation per phase:
+//     exchange U, density (halo = 2 * margin + 2)  -> advectScalar, advectVel
+//     exchange U, density (4)                      -> buoyancy / gravity on owned +- 3, vorticity confinement
+//     exchange U, p (5)                            -> wall mask + (sum, sum^2) on owned planes
+//     all-reduce of the two doubles                -> conv stack on the local slab, velocity update
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // a host that already carries an NCCL (e.g. the one bundled with PyTorch) gets that copy back
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.lib = h;
+#define TFL_NCCL_SYM(name) api.name = (decltype(api.name))dlsym(h, "nccl" #name)
+      TFL_NCCL_SYM(GetUniqueId); TFL_NCCL_SYM(CommInitRank); TFL_NCCL_SYM(CommDestroy); TFL_NCCL_SYM(GroupStart);
+      TFL_NCCL_SYM(GroupEnd); TFL_NCCL_SYM(Send); TFL_NCCL_SYM(Recv); TFL_NCCL_SYM(AllReduce); TFL_NCCL_SYM(GetErrorString);
+#undef TFL_NCCL_SYM
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.GroupStart || !api.GroupEnd || !api.Send ||
+          !api.Recv || !api.AllReduce || !api.GetErrorString)
+        api.lib = nullptr;
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+#define TFL_NCCL(ctx, call)                                                                       \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess) return fail(ctx, "%s: %s", #call, nccl_api()->GetErrorString(r_));     \
+  } while (0)
+
+}  // namespace
+
+struct tfl_slab_sim {
+  int gnz = 0, ny = 0, nx = 0, margin = 2, halo = 6;
+  int rank = 0, world = 1;
+  int z0 = 0, z1 = 0, lo_halo = 0, hi_halo = 0, zoff = 0, nz = 0, own_lo = 0, own_hi = 0;
+  size_t cells = 0, plane = 0;      // local cells / cells per plane
+  tfl_state st;
+  float* U1 = nullptr;
+  double* sums = nullptr;
+  std::vector<void*> owned;
+  cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  size_t bytes_sent[3] = {0, 0, 0};
+};
+
+extern "C" {
+
+int tfl_comm_unique_id(tfl_ctx* ctx, char* id_out) {
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(ctx, "comm: libnccl.so.2 not found");
+  static_assert(sizeof(ncclUniqueId) <= TFL_COMM_ID_BYTES, "unique id fits the ABI buffer");
+  ncclUniqueId id;
+  TFL_NCCL(ctx, nc->GetUniqueId(&id));
+  memset(id_out, 0, TFL_COMM_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int tfl_comm_init(tfl_ctx* ctx, const char* id_bytes, int32_t rank, int32_t world) {
+  DeviceGuard guard_(ctx);
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(ctx, "comm_init: bad rank / world");
+  tfl_comm_destroy(ctx);
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  if (world == 1) return 0;
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(ctx, "comm_init: libnccl.so.2 not found");
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  TFL_NCCL(ctx, nc->CommInitRank(&ctx->comm, world, id, rank));
+  return 0;
+}
+
+int tfl_comm_destroy(tfl_ctx* ctx) {
+  if (ctx && ctx->comm) {
+    DeviceGuard guard_(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    nccl_api()->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  if (ctx) { ctx->comm_rank = 0; ctx->comm_world = 1; }
+  return 0;
+}
+
+void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* s) {
+  DeviceGuard guard_(ctx);
+  if (!s) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (void* p : s->owned) cudaFree(p);
+  for (auto& pr : s->ev) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
+  delete s;
+}
+
+// All host arrays are GLOBAL [c][gnz][ny][nx] fields, identical on every rank; each rank keeps its slab.
+int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32_t margin, const float* flags,
+                        const float* U_bc, const float* U_bc_inv, const float* d_bc, const float* d_bc_inv,
+                        tfl_slab_sim** out) {
+  DeviceGuard guard_(ctx);
+  if (!out || !flags || gnz < 3 || ny < 3 || nx < 3 || margin < 2) return fail(ctx, "slab_sim: bad arguments (margin >= 2)");
+  tfl_slab_sim* s = new tfl_slab_sim();
+  memset(&s->st, 0, sizeof(s->st));
+  s->gnz = gnz; s->ny = ny; s->nx = nx; s->margin = margin; s->halo = 2 * margin + 2;
+  s->rank = ctx->comm_rank; s->world = ctx->comm_world;
+  const int base = gnz / s->world, rem = gnz % s->world;
+  if (s->world > 1 && base < s->halo) { delete s; return fail(ctx, "slab_sim: slabs of %d planes are thinner than the halo (%d)", base, s->halo); }
+  s->z0 = s->rank * base + std::min(s->rank, rem);
+  s->z1 = s->z0 + base + (s->rank < rem ? 1 : 0);
+  s->lo_halo = std::min(s->halo, s->z0);
+  s->hi_halo = std::min(s->halo, gnz - s->z1);
+  s->zoff = s->z0 - s->lo_halo;
+  s->nz = (s->z1 - s->z0) + s->lo_halo + s->hi_halo;
+  s->own_lo = s->lo_halo;
+  s->own_hi = s->lo_halo + (s->z1 - s->z0);
+  s->plane = (size_t)ny * nx;
+  s->cells = s->plane * s->nz;
+  const size_t gcells = s->plane * gnz;
+  auto mk = [&](tfl_grid* g, int nc, const float* host) -> int {
+    g->nb = 1; g->nc = nc; g->nz = s->nz; g->ny = ny; g->nx = nx;
+    void* p = nullptr;
+    if (cudaMalloc(&p, s->cells * nc * 4) != cudaSuccess) return 1;
+    s->owned.push_back(p);
+    g->data = (float*)p;
+    if (!host) return cudaMemset(p, 0, s->cells * nc * 4) != cudaSuccess;
+    for (int c = 0; c < nc; c++)
+      if (cudaMemcpy((float*)p + c * s->cells, host + c * gcells + (size_t)s->zoff * s->plane, s->cells * 4,
+                     cudaMemcpyHostToDevice) != cudaSuccess)
+        return 1;
+    return 0;
+  };
+  int bad = 0;
+  bad |= mk(&s->st.flags, 1, flags);
+  bad |= mk(&s->st.p, 1, nullptr);
+  bad |= mk(&s->st.U, 3, nullptr);
+  bad |= mk(&s->st.density, 1, nullptr);
+  if (U_bc && U_bc_inv) { bad |= mk(&s->st.U_bc, 3, U_bc); bad |= mk(&s->st.U_bc_inv_mask, 3, U_bc_inv); }
+  if (d_bc && d_bc_inv) { bad |= mk(&s->st.density_bc, 1, d_bc); bad |= mk(&s->st.density_bc_inv_mask, 1, d_bc_inv); }
+  void* p = nullptr;
+  bad |= cudaMalloc(&p, s->cells * 3 * 4) != cudaSuccess;
+  if (!bad) { s->owned.push_back(p); s->U1 = (float*)p; }
+  bad |= cudaMalloc(&p, 2 * sizeof(double)) != cudaSuccess;
+  if (!bad) { s->owned.push_back(p); s->sums = (double*)p; }
+  for (auto& pr : s->ev) for (cudaEvent_t& e : pr) bad |= cudaEventCreate(&e) != cudaSuccess;
+  if (bad) { tfl_slab_sim_destroy(ctx, s); return fail(ctx, "slab_sim: allocation failed"); }
+  *out = s;
+  return 0;
+}
+
+// info: zoff, nz, own_lo, own_hi, z0, z1 (local storage and owned planes of this rank)
+int tfl_slab_sim_layout(const tfl_slab_sim* s, tfl_state* state_out, int32_t info[6]) {
+  if (!s) return 1;
+  if (state_out) *state_out = s->st;
+  if (info) { info[0] = s->zoff; info[1] = s->nz; info[2] = s->own_lo; info[3] = s->own_hi; info[4] = s->z0; info[5] = s->z1; }
+  return 0;
+}
+
+// GLOBAL host arrays -> this rank's slab (ghost planes included); any pointer may be NULL.
+int tfl_slab_sim_upload(tfl_ctx* ctx, tfl_slab_sim* s, const float* p, const float* U, const float* density) {
+  DeviceGuard guard_(ctx);
+  if (!s) return fail(ctx, "slab_sim is nil");
+  const size_t gcells = s->plane * s->gnz, off = (size_t)s->zoff * s->plane;
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p) TFL_CUDA(ctx, cudaMemcpy(s->st.p.data, p + off, s->cells * 4, cudaMemcpyHostToDevice));
+  if (density) TFL_CUDA(ctx, cudaMemcpy(s->st.density.data, density + off, s->cells * 4, cudaMemcpyHostToDevice));
+  if (U) for (int c = 0; c < 3; c++)
+    TFL_CUDA(ctx, cudaMemcpy(s->st.U.data + c * s->cells, U + c * gcells + off, s->cells * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// This rank's OWNED planes -> the same planes of GLOBAL host arrays (the rest is left alone).
+int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* s, float* p, float* U, float* density) {
+  DeviceGuard guard_(ctx);
+  if (!s) return fail(ctx, "slab_sim is nil");
+  const size_t gcells = s->plane * s->gnz, goff = (size_t)s->z0 * s->plane, loff = (size_t)s->own_lo * s->plane;
+  const size_t cnt = (size_t)(s->z1 - s->z0) * s->plane * 4;
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p) TFL_CUDA(ctx, cudaMemcpy(p + goff, s->st.p.data + loff, cnt, cudaMemcpyDeviceToHost));
+  if (density) TFL_CUDA(ctx, cudaMemcpy(density + goff, s->st.density.data + loff, cnt, cudaMemcpyDeviceToHost));
+  if (U) for (int c = 0; c < 3; c++)
+    TFL_CUDA(ctx, cudaMemcpy(U + c * gcells + goff, s->st.U.data + c * s->cells + loff, cnt, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Refresh `width` ghost planes on both sides of the listed fields from the neighbours' owned planes.
+int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl_grid*> fields, int width, int phase) {
+  TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][0], ctx->stream));
+  s->bytes_sent[phase] = 0;
+  if (s->world > 1 && width > 0) {
+    if (width > s->halo) return fail(ctx, "slab exchange of %d planes exceeds the halo (%d)", width, s->halo);
+    NcclApi* nc = nccl_api();
+    const size_t cnt = (size_t)width * s->plane;
+    TFL_NCCL(ctx, nc->GroupStart());
+    for (const tfl_grid* f : fields) {
+      for (int c = 0; c < f->nc; c++) {
+        float* base = f->data + (size_t)c * s->cells;
+        if (s->rank > 0) {                        // lower neighbour: my first owned planes go down
+          TFL_NCCL(ctx, nc->Send(base + (size_t)s->own_lo * s->plane, cnt, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+          TFL_NCCL(ctx, nc->Recv(base + (size_t)(s->own_lo - width) * s->plane, cnt, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+          s->bytes_sent[phase] += cnt * 4;
+        }
+        if (s->rank < s->world - 1) {             // upper neighbour
+          TFL_NCCL(ctx, nc->Send(base + (size_t)(s->own_hi - width) * s->plane, cnt, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+          TFL_NCCL(ctx, nc->Recv(base + (size_t)s->own_hi * s->plane, cnt, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+          s->bytes_sent[phase] += cnt * 4;
+        }
+      }
+    }
+    TFL_NCCL(ctx, nc->GroupEnd());
+  }
+  TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][1], ctx->stream));
+  return 0;
+}
+
+struct SlabScope {       // slab placement of the context for the enclosed calls
+  tfl_ctx* ctx;
+  SlabScope(tfl_ctx* c, const tfl_slab_sim* s, int zlo, int zhi) : ctx(c) {
+    c->slab = true; c->zoff = s->zoff; c->gnz = s->gnz; c->zlo = zlo; c->zhi = zhi; c->slab_margin = s->margin;
+  }
+  ~SlabScope() { ctx->slab = false; ctx->slab_margin = 2; }
+};
+
+}  // namespace
+
+extern "C" {
+
+// One tfluids.simulate (convnet path, lib/simulate.lua:175-327) on this rank's slab.  Asynchronous.
+int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cnn* cnn) {
+  DeviceGuard guard_(ctx);
+  if (!s || !mc || !cnn) return fail(ctx, "slab_sim_step: nil argument");
+  if (mc->sim_method != TFL_SIM_CONVNET) return fail(ctx, "slab_sim_step: only simMethod 'convnet' is decomposed");
+  if (s->world != ctx->comm_world || s->rank != ctx->comm_rank) return fail(ctx, "slab_sim_step: communicator changed");
+  const tfl_state& st = s->st;
+  auto bcs = [&]() -> int {
+    if (st.U_bc.data && tfl_apply_bc(ctx, &st.U, &st.U_bc_inv_mask, &st.U_bc)) return 1;
+    if (st.density_bc.data && tfl_apply_bc(ctx, &st.density, &st.density_bc_inv_mask, &st.density_bc)) return 1;
+    return 0;
+  };
+  if (slab_exchange(ctx, s, {&st.U, &st.density}, s->halo, 0)) return 1;
+  {
+    SlabScope scope(ctx, s, s->own_lo, s->own_hi);
+    if (tfl_advect_scalar(ctx, mc->dt, &st.density, &st.U, &st.flags, mc->advection_method, 0, mc->maccormack_strength, nullptr)) return 1;
+    if (tfl_advect_vel(ctx, mc->dt, &st.U, &st.flags, mc->advection_method, mc->maccormack_strength, nullptr)) return 1;
+  }
+  if (bcs()) return 1;
+  if (slab_exchange(ctx, s, {&st.U, &st.density}, 4, 1)) return 1;
+  const int dmax = std::max(s->nx, std::max(s->ny, s->gnz));
+  const double dx = 1.0 / (double)dmax;
+  {
+    // point-wise forces also on the three ghost planes the confinement stencil reads across the cut
+    SlabScope scope(ctx, s, s->own_lo - std::min(3, s->lo_halo), s->own_hi + std::min(3, s->hi_halo));
+    if (mc->buoyancy_scale > 0.0) {
+      const float k = (float)(-(dx / 4.0) * mc->buoyancy_scale);
+      const float gv[3] = {mc->gravity[0] * k, mc->gravity[1] * k, mc->gravity[2] * k};
+      if (tfl_add_buoyancy(ctx, &st.U, &st.flags, &st.density, gv, mc->dt)) return 1;
+    }
+    if (mc->gravity_scale > 0.0) {
+      const float k = (float)((-dx / 4.0) * mc->gravity_scale);
+      const float gv[3] = {mc->gravity[0] * k, mc->gravity[1] * k, mc->gravity[2] * k};
+      if (tfl_add_gravity(ctx, &st.U, &st.flags, gv, mc->dt)) return 1;
+    }
+  }
+  if (mc->vorticity_confinement_amp > 0.0) {
+    SlabScope scope(ctx, s, s->own_lo, s->own_hi);
+    if (tfl_vorticity_confinement(ctx, &st.U, &st.flags, (float)(dx * mc->vorticity_confinement_amp))) return 1;
+  }
+  if (bcs()) return 1;
+  if (slab_exchange(ctx, s, {&st.U, &st.p}, 5, 2)) return 1;
+  tfl_grid u1 = st.U;
+  u1.data = s->U1;
+  {
+    SlabScope scope(ctx, s, s->own_lo, s->own_hi);
+    if (tfl_cnn_stats(ctx, &st.U, &st.flags, &u1, s->sums)) return 1;
+  }
+  TFL_CUDA(ctx, cudaEventRecord(s->ev[3][0], ctx->stream));
+  if (s->world > 1) TFL_NCCL(ctx, nccl_api()->AllReduce(s->sums, s->sums, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  TFL_CUDA(ctx, cudaEventRecord(s->ev[3][1], ctx->stream));
+  {
+    SlabScope scope(ctx, s, s->own_lo, s->own_hi);
+    if (tfl_cnn_project_from_sums(ctx, cnn, &st.p, &u1, &st.flags, s->sums, &st.p, &st.U, mc->normalize_input_threshold)) return 1;
+  }
+  if (bcs()) return 1;
+  return tfl_clamp(ctx, &st.U, -1e6f, 1e6f);
+}
+
+// Device time of the last step's three halo exchanges and of its all-reduce (ms) and the bytes this rank sent in
+// each exchange.  Synchronises.
+int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* s, float ms[4], int64_t bytes[3]) {
+  DeviceGuard guard_(ctx);
+  if (!s) return fail(ctx, "slab_sim is nil");
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; i++) {
+    ms[i] = 0.0f;
+    if (cudaEventElapsedTime(&ms[i], s->ev[i][0], s->ev[i][1]) != cudaSuccess) { cudaGetLastError(); ms[i] = -1.0f; }
+  }
+  for (int i = 0; i < 3; i++) bytes[i] = (int64_t)s->bytes_sent[i];
   return 0;
 }
 

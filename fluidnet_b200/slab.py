@@ -205,6 +205,96 @@ class SlabSimulator:
             dist.broadcast(parts[r], src=r, group=self.group)
 
 
+class NativeSlabSimulator:
+    """The same decomposition with everything inside libtfl.so (tfl_slab_sim_*): the context owns the NCCL
+    communicator, the halo exchanges are ncclSend / ncclRecv straight on the field arrays, one C call per step.
+    This is what a LuaJIT host would drive; torch.distributed is used here only to hand rank 0's NCCL id to the
+    other ranks (any transport would do) and, in `gather`, by the tests."""
+
+    def __init__(self, batch, mconf, model_layers, device, rank=None, world=None, margin=2, group=None):
+        import numpy as np
+        from . import tfluids, model as fmodel, simulate, _lib
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.device = torch.device(device)
+        self.ctx = tfluids.context(self.device)
+        lib = self.ctx.lib
+        ident = [None]
+        if self.world > 1:
+            if self.rank == 0:
+                buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+                self.ctx.check(lib.tfl_comm_unique_id(self.ctx.h, buf))
+                ident = [buf.raw]
+            dist.broadcast_object_list(ident, src=0, group=group)
+        self.ctx.check(lib.tfl_comm_init(self.ctx.h, ident[0] if ident[0] else b"\0" * _lib.COMM_ID_BYTES, self.rank, self.world))
+        self.mconf = dict(mconf)
+        self.mc = simulate.make_mconf(self.mconf)
+        self.model = fmodel.ProjectionModel(model_layers, True, device=self.device,
+                                            normalizeInputThreshold=self.mconf.get("normalizeInputThreshold", 1e-5))
+
+        def host(key):
+            t = batch.get(key)
+            return None if t is None else np.ascontiguousarray(t.numpy() if isinstance(t, torch.Tensor) else t, np.float32)
+
+        self._shape = tuple(batch["flags"].shape)
+        gnz, ny, nx = self._shape[2:]
+        arrs = [host(k) for k in ("flags", "UBC", "UBCInvMask", "densityBC", "densityBCInvMask")]
+        h = C.c_void_p()
+        self.ctx.use_current_stream()
+        self.ctx.check(lib.tfl_slab_sim_create(self.ctx.h, gnz, ny, nx, margin, *[a.ctypes.data if a is not None else None
+                                                                                  for a in arrs], C.byref(h)))
+        self.h = h
+        self.ctx.check(lib.tfl_slab_sim_upload(self.ctx.h, self.h, host("pDiv").ctypes.data, host("UDiv").ctypes.data,
+                                               host("density").ctypes.data))
+        info = (C.c_int32 * 6)()
+        lib.tfl_slab_sim_layout(self.h, None, info)
+        self.zoff, self.nz, self.own_lo, self.own_hi, self.z0, self.z1 = list(info)
+
+    def step(self):
+        self.ctx.use_current_stream()
+        self.ctx.check(self.ctx.lib.tfl_slab_sim_step(self.ctx.h, self.h, C.byref(self.mc), self.model.h))
+
+    def exchange_stats(self):
+        """(ms of the three halo exchanges and the all-reduce of the last step, bytes sent per exchange)."""
+        ms, by = (C.c_float * 4)(), (C.c_int64 * 3)()
+        self.ctx.check(self.ctx.lib.tfl_slab_sim_exchange_stats(self.ctx.h, self.h, ms, by))
+        return list(ms), list(by)
+
+    def check(self):
+        f = torch.tensor([self.ctx.trace_faults()], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(f, group=self.group)
+        if f.item() != 0:
+            raise RuntimeError("z-slab halo too small for the current velocities (%d faults): raise `margin`"
+                               % int(f.item()))
+
+    def download(self):
+        """Global numpy arrays holding THIS rank's owned planes (zeros elsewhere)."""
+        import numpy as np
+        b, _, gnz, ny, nx = self._shape
+        p = np.zeros((1, 1, gnz, ny, nx), np.float32)
+        U = np.zeros((1, 3, gnz, ny, nx), np.float32)
+        d = np.zeros((1, 1, gnz, ny, nx), np.float32)
+        self.ctx.check(self.ctx.lib.tfl_slab_sim_download(self.ctx.h, self.h, p.ctypes.data, U.ctypes.data, d.ctypes.data))
+        return {"pDiv": p, "UDiv": U, "density": d}
+
+    def gather(self, key):
+        """Global tensor assembled from every rank's owned planes (on every rank, CPU)."""
+        mine = torch.from_numpy(self.download()[key])
+        if self.world > 1:
+            t = mine.to(self.device)
+            dist.all_reduce(t, group=self.group)          # owned planes are disjoint, the rest is zero
+            mine = t.cpu()
+        return mine
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tfl_slab_sim_destroy(self.ctx.h, self.h)
+            self.h = None
+        self.ctx.lib.tfl_comm_destroy(self.ctx.h)
+
+
 def run_lockstep(sims):
     """Advance several SlabSimulators of ONE decomposition that live in the same process (tests:
     the whole multi-rank logic on a single GPU).  Halo requests are served by direct copies between

@@ -268,6 +268,32 @@ void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs);
 int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
                       const tfl_mconf* mconf, tfl_cnn* cnn);
 
+/* ---- one domain in z-slabs over the GPUs of a node (no counterpart in the reference, which is single-GPU;
+ * SURVEY.md section 8e).  One process and one context per GPU.  The context owns the NCCL communicator
+ * (libnccl.so.2 is loaded on demand); rank 0 makes an id, the host application distributes its
+ * TFL_COMM_ID_BYTES bytes to every rank by its own means, every rank calls tfl_comm_init. */
+#define TFL_COMM_ID_BYTES 128
+int tfl_comm_unique_id(tfl_ctx* ctx, char* id_out /* TFL_COMM_ID_BYTES */);
+int tfl_comm_init(tfl_ctx* ctx, const char* id_bytes, int32_t rank, int32_t world);   /* world 1: no NCCL */
+int tfl_comm_destroy(tfl_ctx* ctx);
+/* Rank r keeps planes [z0, z1) of a [gnz][ny][nx] domain plus 2 * margin + 2 ghost planes per interior side
+ * (margin = planes a backward trace may reach = ceil(max|u| dt) + 1, >= 2).  The host arrays are GLOBAL
+ * [c][gnz][ny][nx] fields, identical on every rank; the BC pointers may be NULL. */
+typedef struct tfl_slab_sim tfl_slab_sim;
+int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32_t margin, const float* flags,
+                        const float* U_bc, const float* U_bc_inv_mask, const float* density_bc,
+                        const float* density_bc_inv_mask, tfl_slab_sim** out);
+void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* sim);
+/* Device views of the local slab and info = {z offset of local plane 0, local planes, first / past-last owned
+ * local plane, z0, z1}. */
+int tfl_slab_sim_layout(const tfl_slab_sim* sim, tfl_state* state_out, int32_t info[6]);
+int tfl_slab_sim_upload(tfl_ctx* ctx, tfl_slab_sim* sim, const float* p, const float* U, const float* density);
+int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* sim, float* p, float* U, float* density);
+/* One tfluids.simulate (convnet path) on this rank's slab: three neighbour halo exchanges (ncclSend / ncclRecv
+ * straight from and into the field arrays, one NCCL group per phase) and one 2-double all-reduce.  Asynchronous.
+ * A trace that leaves the local slab (margin too small) raises tfl_trace_faults. */
+int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
+int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* sim, float ms[4], int64_t bytes[3]);
 #ifdef __cplusplus
 }
 #endif

@@ -57,17 +57,18 @@ def _problem(n):
     return batch, mconf, synth.make_model(True)
 
 
-def _worker(rank, world, port, n, steps, q):
+def _worker(rank, world, port, n, steps, q, native=False):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
         from fluidnet_b200 import simulate, model as fmodel
-        from fluidnet_b200.slab import SlabSimulator
+        from fluidnet_b200.slab import SlabSimulator, NativeSlabSimulator
         batch, mconf, mnp = _problem(n)
         tb = {k: torch.from_numpy(v) for k, v in batch.items()}
-        sim = SlabSimulator(tb, mconf, mnp["layers"], torch.device("cuda", rank), rank, world)
+        sim = (NativeSlabSimulator if native else SlabSimulator)(tb, mconf, mnp["layers"], torch.device("cuda", rank),
+                                                               rank, world)
         for _ in range(steps):
             sim.step()
         sim.check()
@@ -93,15 +94,16 @@ def _worker(rank, world, port, n, steps, q):
         raise
 
 
-@pytest.mark.parametrize("n,steps", [(48, 2)])
-def test_two_gpu_slab_matches_single_gpu(n, steps):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+@pytest.mark.parametrize("native", [False, True], ids=["torch_exchange", "library_nccl"])
+@pytest.mark.parametrize("world,n,steps", [(2, 48, 2), (4, 64, 2)])
+def test_multi_gpu_slab_matches_single_gpu(world, n, steps, native):
+    """native: the whole decomposed step inside libtfl.so (tfl_slab_sim_step, NCCL owned by the context)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, steps, q, native)) for r in range(world)]
     for p in procs:
         p.start()
     res = _collect(procs, q, 150)
@@ -127,6 +129,30 @@ def test_single_rank_slab_driver_matches_fused_step():
         got = sim.gather(k)
         err = (got - want).abs().max().item()
         assert err <= 1e-6 * max(want.abs().max().item(), 1e-6), (k, err)
+
+
+def test_single_rank_library_slab_step_matches_fused_step():
+    """tfl_slab_sim_* with one rank: the C driver of the decomposed step (uploads, slab placement, the split
+    projection, downloads) against the fused single-GPU step, no NCCL involved."""
+    from fluidnet_b200 import simulate, model as fmodel
+    from fluidnet_b200.slab import NativeSlabSimulator
+    batch, mconf, mnp = _problem(32)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    sim = NativeSlabSimulator(tb, mconf, mnp["layers"], torch.device("cuda", 0), rank=0, world=1)
+    gb = {k: v.cuda() for k, v in tb.items()}
+    gm = fmodel.ProjectionModel(mnp["layers"], True)
+    for _ in range(2):
+        sim.step()
+        simulate.simulate_fused(None, mconf, gb, gm)
+    sim.check()
+    ms, by = sim.exchange_stats()
+    assert by == [0, 0, 0] and all(m >= 0 for m in ms)
+    for k in ("density", "UDiv", "pDiv"):
+        want = gb[k].cpu()
+        got = sim.gather(k)
+        err = (got - want).abs().max().item()
+        assert err <= 1e-6 * max(want.abs().max().item(), 1e-6), (k, err)
+    sim.close()
 
 
 @pytest.mark.parametrize("world,n,steps", [(2, 48, 2), (3, 48, 1)])
