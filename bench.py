@@ -540,4 +540,12 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # The contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version there when a
+    # communicator is created) are sent to stderr; only print() below reaches the real stdout.
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w")
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)
