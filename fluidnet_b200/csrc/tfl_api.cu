@@ -679,6 +679,16 @@ int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_gr
   int iter = 0;
   const bool need_every = p_tol > 0.0f;     // residual < pTol can only trigger for pTol > 0
   std::vector<double> h(g.nb);
+  // A fixed number of sweeps on an L2-resident grid: all but the last inside one cooperative kernel (sweep 0
+  // reads p_prev and writes p, as the loop below does); the loop then runs the last sweep and the residual.
+  if (!need_every && max_iter > 2) {
+    const int fused = max_iter - 1;
+    if (launch_jacobi_sweeps(mask, div->data, p_prev, p->data, g, fused, st)) {
+      ctx->launches += 1;
+      iter = fused;
+      if (fused & 1) { cur = p_prev; prev = p->data; }        // the last fused sweep wrote p
+    }
+  }
   for (;;) {
     launch_jacobi_iter(mask, div->data, prev, cur, g, st);
     ctx->launches += 1;

@@ -54,6 +54,8 @@ template <typename FT>
 void launch_jacobi_mask(const FT* flags, unsigned char* mask, const Geo& g, cudaStream_t st);
 void launch_jacobi_iter(const unsigned char* mask, const float* div, const float* prev, float* cur,
                         const Geo& g, cudaStream_t st);
+bool launch_jacobi_sweeps(const unsigned char* mask, const float* div, float* pa, float* pb, const Geo& g, int sweeps,
+                          cudaStream_t st);
 void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st);
 // changed: optional device word that is OR-ed with 1 when a byte differs from what `o` held before.
 void launch_flags_to_u8(const float* f, unsigned char* o, long long n, int* changed, cudaStream_t st);

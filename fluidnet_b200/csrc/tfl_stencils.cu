@@ -11,6 +11,8 @@
 //   Jacobi         generic/tfluids.cu:1765-1927      emptyDomain generic/tfluids.cc:136-172
 //   flagsToOccupancy generic/tfluids.cu:355-401
 #include <algorithm>
+#include <cstdlib>
+#include <cooperative_groups.h>
 #include "tfl_device.cuh"
 #include "tfl_advect.cuh"
 #include "tfl_kernels.h"
@@ -847,6 +849,101 @@ k_jacobi_march(const unsigned char* __restrict__ mask, const float* __restrict__
   }
 }
 
+// All sweeps in ONE kernel with the CTA's cells resident on the SM.  A CTA owns a 128 x 8 x kJZ block for the
+// whole solve (cooperative launch: every CTA stays resident): its p values live in registers from sweep to
+// sweep, div and the block's y-rows in shared memory, and per sweep only the block's halo (two z planes, two
+// y rows per plane, the x neighbours of wider grids) is read from L2 -- written there by the neighbouring CTAs
+// before the grid-wide barrier that separates the sweeps.  For grids whose fields sit in L2 (128^3: 8 MB per
+// field) the one-kernel-per-sweep version spent most of a sweep on the launch boundary and on L2 latency in
+// its plane-by-plane march; here a sweep is one halo round trip, ~500 instructions per thread and the barrier.
+// p is read with ld.global.cg (L1 is not coherent across CTAs).  Same per-cell expression (bit-identical).
+constexpr int kJZ = 4;
+__global__ void __launch_bounds__(256, 4)
+k_jacobi_resident(const unsigned char* __restrict__ mask, const float* __restrict__ div, float* pa, float* pb, Geo g,
+                  int sweeps) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  extern __shared__ float4 jsm[];
+  float4 (*rows)[kJY + 2][32] = reinterpret_cast<float4 (*)[kJY + 2][32]>(jsm);               // [kJZ][kJY + 2][32]
+  float4 (*dvs)[kJY][32] = reinterpret_cast<float4 (*)[kJY][32]>(jsm + kJZ * (kJY + 2) * 32);   // [kJZ][kJY][32]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = (blockIdx.x * 32 + tx) * 4;
+  const int j = blockIdx.y * kJY + ty;
+  const int nchunks = (g.nz + kJZ - 1) / kJZ;
+  const int b = blockIdx.z / nchunks;
+  const int k0 = (blockIdx.z % nchunks) * kJZ;
+  const int np = min(kJZ, g.nz - k0);                      // planes of this block
+  const int sy = g.nx, sz = g.nx * g.ny;
+  const long long base = b * g.n + (long long)k0 * sz + (long long)j * sy + i0;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool has_left = tx == 0 && i0 > 0, has_right = tx == 31 && i0 + 4 < g.nx;
+  unsigned m4[kJZ];
+  float4 pc[kJZ];
+#pragma unroll
+  for (int k = 0; k < kJZ; k++) {
+    const bool in = k < np;
+    m4[k] = in ? __ldg((const unsigned*)(mask + base + (long long)k * sz)) : 0x01010101u;
+    dvs[k][ty][tx] = in ? __ldg((const float4*)(div + base + (long long)k * sz)) : zero4;
+    pc[k] = in ? __ldcg((const float4*)(pa + base + (long long)k * sz)) : zero4;
+  }
+  for (int s = 0; s < sweeps; s++) {
+    const float* prev = (s & 1) ? pb : pa;                 // sweep 0 reads pa and writes pb
+    float* cur = (s & 1) ? pa : pb;
+    // halo of the block, all requests in flight together
+    const float4 zlo = k0 > 0 ? __ldcg((const float4*)(prev + base - sz)) : zero4;
+    const float4 zhi = k0 + np < g.nz ? __ldcg((const float4*)(prev + base + (long long)np * sz)) : zero4;
+    float left[kJZ], right[kJZ];
+#pragma unroll
+    for (int k = 0; k < kJZ; k++) {
+      const long long c = base + (long long)k * sz;
+      const bool in = k < np;
+      if (ty == 0) rows[k][0][tx] = (in && j > 0) ? __ldcg((const float4*)(prev + c - sy)) : zero4;
+      if (ty == kJY - 1) rows[k][kJY + 1][tx] = (in && j + 1 < g.ny) ? __ldcg((const float4*)(prev + c + sy)) : zero4;
+      left[k] = (in && has_left) ? __ldcg(prev + c - 1) : 0.0f;
+      right[k] = (in && has_right) ? __ldcg(prev + c + 4) : 0.0f;
+      rows[k][ty + 1][tx] = pc[k];
+    }
+    __syncthreads();
+    float4 below = zlo;
+#pragma unroll
+    for (int k = 0; k < kJZ; k++) {
+      const float4 ctr = pc[k];
+      const float4 above = k + 1 < kJZ ? (k + 1 < np ? pc[k + 1] : zhi) : zhi;
+      float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const unsigned mm = m4[k];
+      float lf = __shfl_up_sync(0xffffffffu, ctr.w, 1);        // every lane takes part, whatever its mask
+      float rt = __shfl_down_sync(0xffffffffu, ctr.x, 1);
+      if (tx == 0) lf = left[k];
+      if (tx == 31) rt = right[k];
+      if ((mm & 0x01010101u) != 0x01010101u) {
+        const float4 ym = rows[k][ty][tx], yp = rows[k][ty + 2][tx], dv = dvs[k][ty][tx];
+        const float pcv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+        const float xm[4] = {lf, ctr.x, ctr.y, ctr.z};
+        const float xp[4] = {ctr.y, ctr.z, ctr.w, rt};
+        const float ymv[4] = {ym.x, ym.y, ym.z, ym.w}, ypv[4] = {yp.x, yp.y, yp.z, yp.w};
+        const float zmv[4] = {below.x, below.y, below.z, below.w}, zpv[4] = {above.x, above.y, above.z, above.w};
+        const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const unsigned m = (mm >> (8 * q)) & 0xFFu;
+          if (m & 1) continue;
+          const float p1 = (m & 2) ? pcv[q] : xm[q];
+          const float p2 = (m & 4) ? pcv[q] : xp[q];
+          const float p3 = (m & 8) ? pcv[q] : ymv[q];
+          const float p4 = (m & 16) ? pcv[q] : ypv[q];
+          const float p5 = (m & 32) ? pcv[q] : zmv[q];
+          const float p6 = (m & 64) ? pcv[q] : zpv[q];
+          out[q] = (p1 + p2 + p3 + p4 + p5 + p6 + dvv[q]) / 6.0f;
+        }
+      }
+      const float4 o4 = make_float4(out[0], out[1], out[2], out[3]);
+      if (k < np) *(float4*)(cur + base + (long long)k * sz) = o4;
+      pc[k] = o4;
+      below = ctr;
+    }
+    grid.sync();                                           // also orders the shared rows against the next sweep
+  }
+}
+
 // sum over one batch element of (a - b)^2, accumulated in double: out[b] += ...
 __global__ void k_sqdiff(const float* __restrict__ a, const float* __restrict__ bb, long long n,
                          double* __restrict__ out) {
@@ -1045,6 +1142,42 @@ void launch_jacobi_iter(const unsigned char* mask, const float* div, const float
     return;
   }
   TFL_LAUNCH3(k_jacobi_iter, float, g, st, mask, div, prev, cur, g);
+}
+// `sweeps` Jacobi sweeps in ONE cooperative launch: sweep 0 reads pa and writes pb, sweep 1 the other way, ...
+// (the result is in pb for an odd count).  Returns false when the shape / device does not qualify (the caller
+// then launches one kernel per sweep).
+bool launch_jacobi_sweeps(const unsigned char* mask, const float* div, float* pa, float* pb, const Geo& g, int sweeps,
+                          cudaStream_t st) {
+  const bool aligned = ((uintptr_t)mask % 4 == 0) && ((uintptr_t)div % 16 == 0) && ((uintptr_t)pa % 16 == 0) &&
+                       ((uintptr_t)pb % 16 == 0);
+  // fields that sit in L2; larger grids are bandwidth-bound per sweep and do not fit the SMs
+  if (!g.is3d || !aligned || g.nx % 128 != 0 || g.ny % kJY != 0 || g.nz < 4 || g.zlo != 0 || g.zhi != g.nz ||
+      g.n * g.nb > (3LL << 20) || sweeps < 2)
+    return false;
+  const int smem = (kJZ * (kJY + 2) * 32 + kJZ * kJY * 32) * (int)sizeof(float4);
+  static int capacity = -1;          // resident CTAs of this kernel on the device
+  if (capacity < 0) {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    capacity = 0;
+    if (coop && cudaFuncSetAttribute(k_jacobi_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_resident, 256, smem) == cudaSuccess)
+      capacity = sms * per_sm;
+    cudaGetLastError();
+  }
+  const int nch = (g.nz + kJZ - 1) / kJZ;
+  const long long ctas = (long long)(g.nx / 128) * (g.ny / kJY) * nch * g.nb;
+  if (ctas > capacity) return false;
+  dim3 block(32, kJY, 1), grid(g.nx / 128, g.ny / kJY, nch * g.nb);
+  Geo gg = g;
+  void* args[] = {(void*)&mask, (void*)&div, (void*)&pa, (void*)&pb, (void*)&gg, (void*)&sweeps};
+  if (cudaLaunchCooperativeKernel((const void*)k_jacobi_resident, grid, block, args, smem, st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
 }
 void launch_sqdiff(const float* a, const float* b, long long n, int nb, double* out, cudaStream_t st) {
   long long blocks = (n + 1023) / 1024;
