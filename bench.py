@@ -345,10 +345,30 @@ def main():
             torch.cuda.synchronize()
             return sum(a.elapsed_time(b) for a, b in evs), ctx.launch_count() - lc0
 
+        def timed_graph_steps(state, steps):
+            """The same step replayed from a CUDA graph (tfl_step_graph_*): one launch per step."""
+            graph = simulate.StepGraph(mconf, state, gm)
+            for _ in range(2):
+                graph.launch()
+            stream.synchronize()
+            evs = []
+            for _ in range(steps):
+                flush.fill_(0.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                graph.launch()
+                e1.record(stream)
+                evs.append((e0, e1))
+            stream.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs)
+            graph.close()
+            return ms
+
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         total_ms, launches = timed_steps(gb, args.steps, max(args.warmup, 3))
+        graph_ms = timed_graph_steps(gb, args.steps)
         # trace-length regime of the timed steps (the advection cost is data dependent)
         max_u_dt = float(gb["UDiv"].abs().max().item()) * mconf["dt"]
         if world > 1:
@@ -359,6 +379,10 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t.item()
+        tg = torch.tensor([graph_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        graph_ms = tg.item()
         assert ctx.trace_faults() == 0, "line traces left the domain / hit a hard-error path"
 
         # ---- SURVEY.md 8(d) variant: uniform-random +-2 velocity (incoherent gathers), same step ----
@@ -518,6 +542,8 @@ def main():
                    "l2": "256 MB buffer written between timed steps (L2 flush)",
                    "velocity": "band-limited (4 Fourier modes per component), +-2 cells/s at step 0",
                    "max_u_dt_cells_at_end": max_u_dt},
+        "graph": {"value": world * 1000.0 * args.steps / graph_ms, "unit": "steps/s", "ms_per_step": graph_ms / args.steps,
+                  "what": "the same step replayed from a CUDA graph captured with tfl_step_graph_create (one launch per step)"},
         "variant_random_velocity": variant,
         "hbm_gbs_algorithmic": BYTES_PER_VOXEL_STEP * n ** 3 / (ms * 1e-3) / 1e9,
         "e2e": {"value": world * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": bytes_io,

@@ -4,6 +4,7 @@
 // and tfl_cnn*.cu on the context's stream.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <nccl.h>      // types and prototypes only: libnccl is loaded on demand (dlopen), see NcclApi
 #include <stdarg.h>
 #include <stdio.h>
@@ -98,6 +99,13 @@ struct tfl_cnn {
 
 // Every entry point runs on the context's device whatever the caller's current device is, and leaves the
 // caller's current device as it found it (a host with several contexts / GPUs in one thread).
+// One NVTX range per entry point (named after the function): nsys / ncu --nvtx timelines show the operators.
+// nvtx3 is header-only and costs a null-pointer test when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct DeviceGuard {
   int prev = -1;
   bool switched = false;
@@ -355,6 +363,7 @@ int tfl_create(tfl_ctx** out, int device) {
 
 void tfl_destroy(tfl_ctx* ctx) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -380,6 +389,7 @@ const char* tfl_last_error(const tfl_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int tfl_set_stream(tfl_ctx* ctx, void* s) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!ctx) return 1;
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (s == nullptr) {
@@ -397,6 +407,7 @@ int tfl_set_stream(tfl_ctx* ctx, void* s) {
 void* tfl_get_stream(tfl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int tfl_sync(tfl_ctx* ctx) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -404,6 +415,7 @@ int64_t tfl_launch_count(const tfl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   unsigned long long v = 0;
   TFL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->counters, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -414,6 +426,7 @@ int tfl_trace_faults(tfl_ctx* ctx, int64_t* count, int reset) {
 
 int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo, int32_t z_hi) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (global_nz <= 0) { ctx->slab = false; return 0; }
   ctx->slab = true;
   ctx->zoff = z_offset; ctx->gnz = global_nz; ctx->zlo = z_lo; ctx->zhi = z_hi;
@@ -422,6 +435,7 @@ int tfl_set_slab(tfl_ctx* ctx, int32_t z_offset, int32_t global_nz, int32_t z_lo
 
 int tfl_set_slab_margin(tfl_ctx* ctx, int32_t planes) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (planes < 0) return fail(ctx, "slab margin must be >= 0");
   ctx->slab_margin = planes;
   return 0;
@@ -429,36 +443,43 @@ int tfl_set_slab_margin(tfl_ctx* ctx, int32_t planes) {
 
 int tfl_alloc(tfl_ctx* ctx, size_t bytes, void** p) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaMalloc(p, bytes));
   return 0;
 }
 int tfl_free(tfl_ctx* ctx, void* p) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaFree(p));
   return 0;
 }
 int tfl_alloc_host(tfl_ctx* ctx, size_t bytes, void** p) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaMallocHost(p, bytes));
   return 0;
 }
 int tfl_free_host(tfl_ctx* ctx, void* p) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaFreeHost(p));
   return 0;
 }
 int tfl_memcpy_h2d(tfl_ctx* ctx, void* d, const void* h, size_t bytes) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int tfl_memcpy_d2h(tfl_ctx* ctx, void* h, const void* d, size_t bytes) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 int tfl_memcpy_d2d(tfl_ctx* ctx, void* dst, const void* src, size_t bytes) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   TFL_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
@@ -468,6 +489,7 @@ int tfl_memcpy_d2d(tfl_ctx* ctx, void* dst, const void* src, size_t bytes) {
 // ---------------------------------------------------------------------------------------
 int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags")) return 1;
   if (!((!is_3d || (ctx->slab ? ctx->gnz : flags->nz) >= bnd * 2 + 1) && flags->ny >= bnd * 2 + 1 &&
         flags->nx >= bnd * 2 + 1))
@@ -481,6 +503,7 @@ int tfl_empty_domain(tfl_ctx* ctx, const tfl_grid* flags, int is_3d, int bnd) {
 
 int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* occ, int64_t* bad) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, occ, "occupancy")) return 1;
   if (!same_spatial(flags, occ)) return fail(ctx, "Size mismatch");
   const long long n = (long long)flags->nb * flags->nz * flags->ny * flags->nx;
@@ -499,6 +522,7 @@ int tfl_flags_to_occupancy(tfl_ctx* ctx, const tfl_grid* flags, const tfl_grid* 
 
 int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   Geo g;
   if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
@@ -510,6 +534,7 @@ int tfl_set_wall_bcs_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* fl
 int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags,
                                     const tfl_grid* div) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, div, "UDiv")) return 1;
   if (!same_spatial(flags, div)) return fail(ctx, "Size mismatch");
   Geo g;
@@ -521,6 +546,7 @@ int tfl_velocity_divergence_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_g
 
 int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p")) return 1;
   if (!same_spatial(flags, p)) return fail(ctx, "Size mismatch");
   Geo g;
@@ -533,6 +559,7 @@ int tfl_velocity_update_forward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid*
 int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* density,
                      const float gravity[3], float dt) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, density, "density"))
     return 1;
   if (!same_spatial(flags, density)) return fail(ctx, "Size mismatch");
@@ -549,6 +576,7 @@ int tfl_add_buoyancy(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, con
 
 int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const float gravity[3], float dt) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   if (!gravity) return fail(ctx, "gravity must be a 3D vector (even in 2D).");
   Geo g;
@@ -562,6 +590,7 @@ int tfl_add_gravity(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, cons
 
 int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, float strength) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   Geo g;
   if (make_geo(ctx, flags, U->nc == 3, &g)) return 1;
@@ -578,6 +607,7 @@ int tfl_vorticity_confinement(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* f
 int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid* U, const tfl_grid* flags,
                       int method, int sample_outside_fluid, float strength, const tfl_grid* s_dst) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, s, "s") || check_vel(ctx, U, flags)) return 1;
   if (!same_spatial(flags, s)) return fail(ctx, "Size mismatch");
   if (s_dst && (check_scalar(ctx, s_dst, "sDst") || !same_spatial(s_dst, s))) return fail(ctx, "Size mismatch");
@@ -618,6 +648,7 @@ int tfl_advect_scalar(tfl_ctx* ctx, float dt, const tfl_grid* s, const tfl_grid*
 int tfl_advect_vel(tfl_ctx* ctx, float dt, const tfl_grid* U, const tfl_grid* flags, int method,
                    float strength, const tfl_grid* U_dst) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags)) return 1;
   if (U_dst && (check_vel(ctx, U_dst, flags) || U_dst->nc != U->nc)) return fail(ctx, "Size mismatch");
   if (method < 0 || method > 5) return fail(ctx, "advection method not supported");
@@ -655,6 +686,7 @@ int tfl_solve_linear_system_jacobi(tfl_ctx* ctx, const tfl_grid* p, const tfl_gr
                                    const tfl_grid* div, int is_3d, float p_tol, int max_iter,
                                    float* residual, int* iterations) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
   if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -727,6 +759,7 @@ int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
                                 int is_3d, int precond, float tol, int max_iter, float* residual,
                                 int* iterations) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p") || check_scalar(ctx, div, "div")) return 1;
   if (!same_spatial(flags, p) || !same_spatial(flags, div)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -745,6 +778,7 @@ int tfl_solve_linear_system_pcg(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
 
 int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid* flags, int is_3d) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p, "p")) return 1;
   if (!same_spatial(flags, p)) return fail(ctx, "size mismatch");
   if (!is_3d && flags->nz != 1) return fail(ctx, "d > 1 for a 2D domain");
@@ -759,6 +793,7 @@ int tfl_normalize_pressure_mean(tfl_ctx* ctx, const tfl_grid* p, const tfl_grid*
 
 int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!in || !out || !in->data || !out->data) return fail(ctx, "ERROR: input and output must be dim 5");
   if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
   if (out->nb != in->nb || out->nc != in->nc || out->nz != in->nz * ratio || out->ny != in->ny * ratio ||
@@ -771,6 +806,7 @@ int tfl_volumetric_up_sampling_nearest_forward(tfl_ctx* ctx, int ratio, const tf
 
 int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is_3d, const tfl_grid* dst) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!src || !dst || !src->data || !dst->data) return fail(ctx, "ERROR: src and dst must be dim 5");
   if (!same_spatial(src, dst) || src->nc != dst->nc) return fail(ctx, "size mismatch");
   if (blur_rad <= 0) return fail(ctx, "blurRad must be a positive, non-zero integer");   // init.lua:586-587
@@ -796,6 +832,7 @@ int tfl_rectangular_blur(tfl_ctx* ctx, const tfl_grid* src, int blur_rad, int is
 
 int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_rad, int is_3d, const tfl_grid* dst) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, dst, "dst")) return 1;
   if (!same_spatial(flags, dst)) return fail(ctx, "size mismatch");
   if (search_rad <= 0) return fail(ctx, "searchRad must be a positive, non-zero integer");   // init.lua:609-610
@@ -809,6 +846,7 @@ int tfl_signed_distance_field(tfl_ctx* ctx, const tfl_grid* flags, int search_ra
 int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* go,
                                      const tfl_grid* gU) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, go, "gradOutput")) return 1;
   if (!gU || !gU->data || gU->nc != U->nc || !same_spatial(gU, U) || !same_spatial(go, flags)) return fail(ctx, "Size mismatch");
   if (ctx->slab) return fail(ctx, "backward operators: single GPU only");
@@ -821,6 +859,7 @@ int tfl_velocity_divergence_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_
 int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid* flags, const tfl_grid* p,
                                  const tfl_grid* go, const tfl_grid* gp) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U, flags) || check_scalar(ctx, p, "p") ||
       check_scalar(ctx, gp, "gradP"))
     return 1;
@@ -836,6 +875,7 @@ int tfl_velocity_update_backward(tfl_ctx* ctx, const tfl_grid* U, const tfl_grid
 int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const tfl_grid* in, const tfl_grid* go,
                                                 const tfl_grid* gi) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!in || !go || !gi || !in->data || !go->data || !gi->data)
     return fail(ctx, "ERROR: input, gradOutput and gradInput must be dim 5");
   if (ratio < 1) return fail(ctx, "ratio must be a positive integer");
@@ -851,6 +891,7 @@ int tfl_volumetric_up_sampling_nearest_backward(tfl_ctx* ctx, int ratio, const t
 // Debug hook (not in include/tfl.h): planes per CTA of the PCG sweep pipeline.
 extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!ctx) return 1;
   ctx->pcg.groups_override = groups;
   return 0;
@@ -858,6 +899,7 @@ extern "C" int tfl_debug_pcg_groups(tfl_ctx* ctx, int groups) {
 
 extern "C" int tfl_debug_pcg_timing(tfl_ctx* ctx, void* dev_buf) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!ctx) return 1;
   ctx->pcg.debug_timing = dev_buf;
   return 0;
@@ -865,6 +907,7 @@ extern "C" int tfl_debug_pcg_timing(tfl_ctx* ctx, void* dev_buf) {
 
 int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, const tfl_grid* bc) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!x || !inv_mask || !bc || !x->data || !inv_mask->data || !bc->data) return fail(ctx, "applyBC: nil tensor");
   if (!same_spatial(x, inv_mask) || !same_spatial(x, bc) || x->nc != inv_mask->nc || x->nc != bc->nc)
     return fail(ctx, "Size mismatch");
@@ -876,6 +919,7 @@ int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, cons
 
 int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!x || !x->data) return fail(ctx, "clamp: nil tensor");
   const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
   launch_clamp(x->data, lo, hi, n, ctx->stream);
@@ -890,6 +934,7 @@ int tfl_cnn_create(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* cin, co
                    const int32_t* ksize, const float* const* weights, const float* const* biases,
                    tfl_cnn** out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   return tfl_cnn_create_graph(ctx, is_3d, n_layers, cin, cout, ksize, nullptr, nullptr, 0, 0, weights, biases, out);
 }
 
@@ -898,6 +943,7 @@ int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* c
                          int nonlin_sigmoid, const float* const* weights, const float* const* biases,
                          tfl_cnn** out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!out || n_layers < 1) return fail(ctx, "cnn: bad arguments");
   // Channels the convolution of layer l really emits: cout * up^d (ConvolutionUpsample, model_utils.lua:74-76).
   std::vector<int32_t> cout_conv(n_layers);
@@ -987,6 +1033,7 @@ int tfl_cnn_create_graph(tfl_ctx* ctx, int is_3d, int n_layers, const int32_t* c
 
 int tfl_cnn_set_mode(tfl_ctx* ctx, tfl_cnn* m, int mode) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!m || mode < 0 || mode > 2) return fail(ctx, "cnn_set_mode: bad arguments");
   if (mode > 0 && !m->tc_ok)
     return fail(ctx, "cnn_set_mode: the tensor-core path covers the 3-D 'default' architecture only");
@@ -1010,6 +1057,7 @@ int tfl_debug_conv_ts_counters(void* dev_buf) { conv_ts_set_debug((long long*)de
 
 void tfl_cnn_destroy(tfl_ctx* ctx, tfl_cnn* m) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!m) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (float* p : m->w) cudaFree(p);
@@ -1155,6 +1203,7 @@ int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_g
                     const tfl_grid* flags, const tfl_grid* p_out, const tfl_grid* U_out, float threshold,
                     float* scale_out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!m) return fail(ctx, "cnn is nil");
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U_div, flags) ||
       check_scalar(ctx, p_out, "p") || check_vel(ctx, U_out, flags))
@@ -1187,6 +1236,7 @@ int tfl_cnn_project(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, const tfl_g
 int tfl_cnn_stats(tfl_ctx* ctx, const tfl_grid* U_div, const tfl_grid* flags, const tfl_grid* U1,
                   double* dev_sums) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (check_scalar(ctx, flags, "flags") || check_vel(ctx, U_div, flags) || check_vel(ctx, U1, flags)) return 1;
   if (!dev_sums) return fail(ctx, "cnn_stats: nil sums");
   Geo g;
@@ -1206,6 +1256,7 @@ int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, c
                               const tfl_grid* flags, const double* dev_sums, const tfl_grid* p_out,
                               const tfl_grid* U_out, float threshold) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!m) return fail(ctx, "cnn is nil");
   if (!m->tc_ok || m->mode == 0) return fail(ctx, "cnn_project_from_sums needs the tensor-core path (3-D default net)");
   if (check_scalar(ctx, flags, "flags") || check_scalar(ctx, p_div, "pDiv") || check_vel(ctx, U1, flags) ||
@@ -1349,6 +1400,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
 
 int tfl_simulate_step(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf* mc, tfl_cnn* cnn) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s || !mc) return fail(ctx, "simulate: nil state / mconf");
   if (check_scalar(ctx, &s->flags, "flags") || check_scalar(ctx, &s->p, "pDiv") || check_vel(ctx, &s->U, &s->flags))
     return 1;
@@ -1428,6 +1480,7 @@ int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_
                         const float* flags, const float* U_bc, const float* U_bc_inv, const float* d_bc,
                         const float* d_bc_inv, tfl_host_sim** out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!out || !flags) return fail(ctx, "host_sim: bad arguments");
   tfl_host_sim* hs = new tfl_host_sim();
   memset(&hs->st, 0, sizeof(hs->st));
@@ -1458,6 +1511,7 @@ int tfl_host_sim_create(tfl_ctx* ctx, int32_t nb, int32_t nz, int32_t ny, int32_
 
 void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!hs) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (void* p : hs->owned) cudaFree(p);
@@ -1467,6 +1521,7 @@ void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs) {
 int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
                       const tfl_mconf* mc, tfl_cnn* cnn) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!hs || !p || !U) return fail(ctx, "host_sim_step: nil buffer");
   cudaStream_t st = ctx->stream;
   tfl_state s = hs->st;
@@ -1588,6 +1643,7 @@ int tfl_comm_unique_id(tfl_ctx* ctx, char* id_out) {
 
 int tfl_comm_init(tfl_ctx* ctx, const char* id_bytes, int32_t rank, int32_t world) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!ctx || world < 1 || rank < 0 || rank >= world) return fail(ctx, "comm_init: bad rank / world");
   tfl_comm_destroy(ctx);
   ctx->comm_rank = rank;
@@ -1604,6 +1660,7 @@ int tfl_comm_init(tfl_ctx* ctx, const char* id_bytes, int32_t rank, int32_t worl
 int tfl_comm_destroy(tfl_ctx* ctx) {
   if (ctx && ctx->comm) {
     DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
     cudaStreamSynchronize(ctx->stream);
     nccl_api()->CommDestroy(ctx->comm);
     ctx->comm = nullptr;
@@ -1614,6 +1671,7 @@ int tfl_comm_destroy(tfl_ctx* ctx) {
 
 void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* s) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (void* p : s->owned) cudaFree(p);
@@ -1626,6 +1684,7 @@ int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32
                         const float* U_bc, const float* U_bc_inv, const float* d_bc, const float* d_bc_inv,
                         tfl_slab_sim** out) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!out || !flags || gnz < 3 || ny < 3 || nx < 3 || margin < 2) return fail(ctx, "slab_sim: bad arguments (margin >= 2)");
   tfl_slab_sim* s = new tfl_slab_sim();
   memset(&s->st, 0, sizeof(s->st));
@@ -1686,6 +1745,7 @@ int tfl_slab_sim_layout(const tfl_slab_sim* s, tfl_state* state_out, int32_t inf
 // GLOBAL host arrays -> this rank's slab (ghost planes included); any pointer may be NULL.
 int tfl_slab_sim_upload(tfl_ctx* ctx, tfl_slab_sim* s, const float* p, const float* U, const float* density) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s) return fail(ctx, "slab_sim is nil");
   const size_t gcells = s->plane * s->gnz, off = (size_t)s->zoff * s->plane;
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1699,6 +1759,7 @@ int tfl_slab_sim_upload(tfl_ctx* ctx, tfl_slab_sim* s, const float* p, const flo
 // This rank's OWNED planes -> the same planes of GLOBAL host arrays (the rest is left alone).
 int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* s, float* p, float* U, float* density) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s) return fail(ctx, "slab_sim is nil");
   const size_t gcells = s->plane * s->gnz, goff = (size_t)s->z0 * s->plane, loff = (size_t)s->own_lo * s->plane;
   const size_t cnt = (size_t)(s->z1 - s->z0) * s->plane * 4;
@@ -1759,6 +1820,7 @@ extern "C" {
 // One tfluids.simulate (convnet path, lib/simulate.lua:175-327) on this rank's slab.  Asynchronous.
 int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cnn* cnn) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s || !mc || !cnn) return fail(ctx, "slab_sim_step: nil argument");
   if (mc->sim_method != TFL_SIM_CONVNET) return fail(ctx, "slab_sim_step: only simMethod 'convnet' is decomposed");
   if (s->world != ctx->comm_world || s->rank != ctx->comm_rank) return fail(ctx, "slab_sim_step: communicator changed");
@@ -1819,6 +1881,7 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
 // each exchange.  Synchronises.
 int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* s, float ms[4], int64_t bytes[3]) {
   DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
   if (!s) return fail(ctx, "slab_sim is nil");
   TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 4; i++) {
@@ -1826,6 +1889,76 @@ int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* s, float ms[4], int6
     if (cudaEventElapsedTime(&ms[i], s->ev[i][0], s->ev[i][1]) != cudaSuccess) { cudaGetLastError(); ms[i] = -1.0f; }
   }
   for (int i = 0; i < 3; i++) bytes[i] = (int64_t)s->bytes_sent[i];
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// The step as a CUDA graph: tfl_simulate_step captured once on the context's stream (both streams of the
+// fused step, their fork / join events, the memsets and the telemetry copy become graph nodes) and replayed
+// with one launch.  Pointers and every host-side choice of the captured call (fused or per-operator path,
+// advection tile halo) are frozen into the graph; results equal tfl_simulate_step's.
+// ---------------------------------------------------------------------------------------
+struct tfl_step_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;       // kernels in one replay
+};
+
+extern "C" {
+
+void tfl_step_graph_destroy(tfl_ctx* ctx, tfl_step_graph* g) {
+  DeviceGuard guard_(ctx);
+  if (!g) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+// Preconditions: the context runs on a non-default stream (tfl_set_stream; the legacy default stream cannot be
+// captured) and one tfl_simulate_step with the same state shapes has already run (scratch buffers are sized
+// then: capturing must not allocate).
+int tfl_step_graph_create(tfl_ctx* ctx, const tfl_state* state, const tfl_mconf* mc, tfl_cnn* cnn, tfl_step_graph** out) {
+  DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
+  if (!out || !state || !mc) return fail(ctx, "step_graph: nil argument");
+  cudaStream_t st = ctx->stream;
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)
+    return fail(ctx, "step_graph: the default stream cannot be captured; give the context a stream (tfl_set_stream)");
+  TFL_CUDA(ctx, cudaStreamSynchronize(st));
+  const long long l0 = ctx->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, "step_graph: cudaStreamBeginCapture failed");
+  }
+  const int rc = tfl_simulate_step(ctx, state, mc, cnn);
+  tfl_step_graph* g = new tfl_step_graph();
+  const cudaError_t e = cudaStreamEndCapture(st, &g->graph);
+  if (rc != 0 || e != cudaSuccess || !g->graph) {
+    cudaGetLastError();
+    const std::string why = rc != 0 ? ctx->err : std::string(cudaGetErrorString(e));
+    tfl_step_graph_destroy(ctx, g);
+    return fail(ctx, "step_graph: capture failed (%s); run tfl_simulate_step once before capturing", why.c_str());
+  }
+  g->launches = ctx->launches - l0;
+  ctx->launches = l0;
+  if (cudaGraphInstantiate(&g->exec, g->graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    tfl_step_graph_destroy(ctx, g);
+    return fail(ctx, "step_graph: cudaGraphInstantiate failed");
+  }
+  *out = g;
+  return 0;
+}
+
+int tfl_step_graph_launch(tfl_ctx* ctx, tfl_step_graph* g) {
+  DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
+  if (!g || !g->exec) return fail(ctx, "step_graph is nil");
+  TFL_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
   return 0;
 }
 

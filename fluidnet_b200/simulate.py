@@ -179,3 +179,32 @@ def simulate_fused(conf, mconf, batch, model=None):
         # one source for the input-scale threshold: the model's (what `simulate` uses through model.forward)
         mc.normalize_input_threshold = float(model.threshold)
     c.check(c.lib.tfl_simulate_step(c.h, C.byref(st), C.byref(mc), model.h if model is not None else None))
+
+
+class StepGraph:
+    """One simulate_fused call captured as a CUDA graph (tfl_step_graph_*): `launch()` replays it on the
+    batch tensors it was captured with.  Needs a non-default current stream and one earlier step."""
+
+    def __init__(self, mconf, batch, model=None):
+        p = batch["pDiv"]
+        if (mconf.get("simMethod") or "convnet") != "convnet" and batch.get("div") is None:
+            batch["div"] = torch.empty_like(p)
+        self.ctx = tfluids._ctx_for(p)
+        self.batch, self.model = batch, model          # keep the captured tensors alive
+        st = make_state(batch)
+        mc = make_mconf(mconf)
+        if model is not None:
+            mc.normalize_input_threshold = float(model.threshold)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tfl_step_graph_create(self.ctx.h, C.byref(st), C.byref(mc),
+                                                          model.h if model is not None else None, C.byref(h)))
+        self.h = h
+
+    def launch(self):
+        self.ctx.use_current_stream()
+        self.ctx.check(self.ctx.lib.tfl_step_graph_launch(self.ctx.h, self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tfl_step_graph_destroy(self.ctx.h, self.h)
+            self.h = None

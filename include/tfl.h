@@ -268,6 +268,15 @@ void tfl_host_sim_destroy(tfl_ctx* ctx, tfl_host_sim* hs);
 int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float* density,
                       const tfl_mconf* mconf, tfl_cnn* cnn);
 
+/* The step as a CUDA graph: tfl_simulate_step captured once (kernels of both internal streams, memsets, the
+ * telemetry copy) and replayed with one launch per step.  The context must run on a non-default stream and one
+ * tfl_simulate_step with the same state must have run before (capturing cannot allocate).  State pointers,
+ * mconf and every host-side choice of the captured call are frozen into the graph. */
+typedef struct tfl_step_graph tfl_step_graph;
+int tfl_step_graph_create(tfl_ctx* ctx, const tfl_state* state, const tfl_mconf* mconf, tfl_cnn* cnn,
+                          tfl_step_graph** out);
+int tfl_step_graph_launch(tfl_ctx* ctx, tfl_step_graph* graph);
+void tfl_step_graph_destroy(tfl_ctx* ctx, tfl_step_graph* graph);
 /* ---- one domain in z-slabs over the GPUs of a node (no counterpart in the reference, which is single-GPU;
  * SURVEY.md section 8e).  One process and one context per GPU.  The context owns the NCCL communicator
  * (libnccl.so.2 is loaded on demand); rank 0 makes an id, the host application distributes its

@@ -329,3 +329,41 @@ def test_operators_on_a_non_current_device(orc):
     div = torch.empty_like(fl)
     tfluids.velocityDivergenceForward(U, fl, div)
     assert bits_equal(div.cpu().numpy(), orc.velocityDivergenceForward(c["UDiv"], c["flags"]))
+
+
+def test_step_as_cuda_graph_equals_direct_step(orc):
+    """tfl_step_graph_*: the fused step captured once and replayed gives the bits of the direct call (same
+    kernels), on the convnet and on the Jacobi path; capturing on the default stream is refused."""
+    import torch
+    from fluidnet_b200 import simulate, synth
+    from fluidnet_b200._lib import TflError
+    from gpu_backend import make_gpu_model
+    n = 32
+    flags = synth.make_flags(n, n, n, True, nb=1, geometry=True)
+    U = synth.make_smooth_velocity(flags, True, amp=3.0)
+    orc.setWallBcsForward(U, flags)
+    batch = {"pDiv": np.zeros_like(flags), "UDiv": U, "flags": flags, "density": synth.make_density(flags)}
+    oracle.create_plume_bcs(batch, [1.0], n / 128.0, 0.15)
+    mnp = synth.make_model(True)
+    for sim_method, model in (("convnet", make_gpu_model(mnp)), ("jacobi", None)):
+        mconf = oracle.default_mconf(dt=0.1, maccormackStrength=0.6, buoyancyScale=2.0 * n / 128,
+                                     vorticityConfinementAmp=3.0, simMethod=sim_method, maxIter=12)
+        ga = {k: torch.from_numpy(v.copy()).cuda() for k, v in batch.items()}
+        gb = {k: torch.from_numpy(v.copy()).cuda() for k, v in batch.items()}
+        with pytest.raises(TflError):
+            simulate.simulate_fused(None, mconf, gb, model)       # sizes the scratch buffers ...
+            simulate.StepGraph(mconf, gb, model)                  # ... but the default stream cannot be captured
+        gb = {k: torch.from_numpy(v.copy()).cuda() for k, v in batch.items()}
+        stream = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            simulate.simulate_fused(None, mconf, ga, model)
+            simulate.simulate_fused(None, mconf, gb, model)
+            graph = simulate.StepGraph(mconf, gb, model)          # capture executes nothing
+            for _ in range(2):
+                simulate.simulate_fused(None, mconf, ga, model)
+                graph.launch()
+            stream.synchronize()
+            for k in ("density", "UDiv", "pDiv"):
+                assert torch.equal(ga[k].view(torch.int32), gb[k].view(torch.int32)), (sim_method, k)
+            graph.close()
