@@ -93,7 +93,7 @@ struct tfl_cnn {
   int use_ts = 1;            // mode 2 prefers the TMEM-operand kernel where it applies
   float* tail = nullptr;     // w4[8][8], b4[8], w5[8], b5[1]
   float* act[3] = {nullptr, nullptr, nullptr};   // padded channels-last activation buffers
-  ConvTcGeo act_geo = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  ConvTcGeo act_geo = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 
@@ -1089,18 +1089,25 @@ static int cnn_ensure_act(tfl_ctx* ctx, tfl_cnn* m, const Geo& g) {
 }
 
 // The three 3x3x3 layers (+ fused 1x1x1 tail) on tensor cores: act[0] -> act[1] -> act[2] -> p_net.
-static void run_conv_stack(tfl_cnn* m, float* p_net, cudaStream_t st) {
+// p_lo / p_hi: planes on which p_net is wanted (default all).  Layer l then only has to produce the planes the
+// later layers' 3x3x3 stencils reach from there; on a z-slab that spares most of the ghost planes.
+static void run_conv_stack(tfl_cnn* m, float* p_net, cudaStream_t st, int p_lo = 0, int p_hi = -1) {
   const ConvTcGeo& tg = m->act_geo;
-  if (m->mode == 2 && m->use_ts && conv_ts_supported(tg)) {
+  if (p_hi < 0) p_hi = tg.nz;
+  if (m->mode == 2 && m->use_ts && conv_ts_supported(tg)) {        // (whole slab: this kernel marches over z)
     launch_conv3_ts(m->act[0], m->act[1], nullptr, m->wTS[0], m->b[0], nullptr, 1, 0, tg, st);
     launch_conv3_ts(m->act[1], m->act[2], nullptr, m->wTS[1], m->b[1], nullptr, 2, 0, tg, st);
     launch_conv3_ts(m->act[2], nullptr, p_net, m->wTS[2], m->b[2], m->tail, 2, 1, tg, st);
     return;
   }
   const int split = m->mode == 2 ? 1 : 0;
-  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, tg, st);
-  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, tg, st);
-  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, tg, st);
+  ConvTcGeo g1 = tg, g2 = tg, g3 = tg;
+  g3.z_lo = std::max(0, p_lo);     g3.z_hi = std::min(tg.nz, p_hi);
+  g2.z_lo = std::max(0, p_lo - 1); g2.z_hi = std::min(tg.nz, p_hi + 1);
+  g1.z_lo = std::max(0, p_lo - 2); g1.z_hi = std::min(tg.nz, p_hi + 2);
+  launch_conv3_tc(m->act[0], m->act[1], nullptr, m->wB[split][0], m->b[0], nullptr, 1, 0, split, g1, st);
+  launch_conv3_tc(m->act[1], m->act[2], nullptr, m->wB[split][1], m->b[1], nullptr, 2, 0, split, g2, st);
+  launch_conv3_tc(m->act[2], nullptr, p_net, m->wB[split][2], m->b[2], m->tail, 2, 1, split, g3, st);
 }
 
 static int cnn_project_impl(tfl_ctx* ctx, tfl_cnn* m, const float* p_div, const float* U_div,
@@ -1280,7 +1287,9 @@ int tfl_cnn_project_from_sums(tfl_ctx* ctx, tfl_cnn* m, const tfl_grid* p_div, c
   }
   const ConvTcGeo& tg = m->act_geo;
   launch_cnn_inputs_padded(p_div->data, U1->data, flags->data, scale, m->act[0], tg.px, tg.py, gi, st);
-  run_conv_stack(m, p_net, st);
+  // the velocity update of the computed planes [zlo, zhi) reads p on [zlo - 1, zhi)
+  if (ctx->slab) run_conv_stack(m, p_net, st, g.zlo - 1, g.zhi);
+  else run_conv_stack(m, p_net, st);
   launch_cnn_finish(p_net, U1->data, flags->data, scale, p_out->data, U_out->data, g, st);
   ctx->launches += 6;
   return check_launch(ctx, "cnn_project_from_sums");
@@ -1648,7 +1657,7 @@ int tfl_comm_init(tfl_ctx* ctx, const char* id_bytes, int32_t rank, int32_t worl
   tfl_comm_destroy(ctx);
   ctx->comm_rank = rank;
   ctx->comm_world = world;
-  if (world == 1) return 0;
+  if (world == 1 || !id_bytes) return 0;       // nil id: a rank's workload without its neighbours (profiling)
   NcclApi* nc = nccl_api();
   if (!nc) return fail(ctx, "comm_init: libnccl.so.2 not found");
   ncclUniqueId id;
@@ -1779,7 +1788,7 @@ namespace {
 int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl_grid*> fields, int width, int phase) {
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][0], ctx->stream));
   s->bytes_sent[phase] = 0;
-  if (s->world > 1 && width > 0) {
+  if (s->world > 1 && width > 0 && ctx->comm) {
     if (width > s->halo) return fail(ctx, "slab exchange of %d planes exceeds the halo (%d)", width, s->halo);
     NcclApi* nc = nccl_api();
     const size_t cnt = (size_t)width * s->plane;
@@ -1867,7 +1876,7 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
     if (tfl_cnn_stats(ctx, &st.U, &st.flags, &u1, s->sums)) return 1;
   }
   TFL_CUDA(ctx, cudaEventRecord(s->ev[3][0], ctx->stream));
-  if (s->world > 1) TFL_NCCL(ctx, nccl_api()->AllReduce(s->sums, s->sums, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  if (s->world > 1 && ctx->comm) TFL_NCCL(ctx, nccl_api()->AllReduce(s->sums, s->sums, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   TFL_CUDA(ctx, cudaEventRecord(s->ev[3][1], ctx->stream));
   {
     SlabScope scope(ctx, s, s->own_lo, s->own_hi);

@@ -163,7 +163,7 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
   // ---- stage the input box ------------------------------------------------------------
   const long long plane_g = (long long)(g.nz + 2) * g.py * g.px;            // float4 per global plane
   const long long batch_g = plane_g * 2;
-  const int x0 = tx * 30, y0 = ty * T::TY, z0 = tzb * T::TZ;                  // padded coords of box origin
+  const int x0 = tx * 30, y0 = ty * T::TY, z0 = g.z_lo + tzb * T::TZ;         // padded coords of box origin
   const float4* inb = in + b * batch_g;
   if (!SPLIT) {
     for (int idx = tid; idx < T::POS; idx += kThreads) {
@@ -314,7 +314,7 @@ k_conv3_tc(const float4* __restrict__ in, float4* __restrict__ out, float* __res
       const int xg = x0 + lane - 1;                         // unpadded coordinates of this lane's voxel
       const int yg = y0 + 4 * (t % T::RB) + q;
       const int zg = z0 + t / T::RB;
-      const bool valid = lane >= 1 && lane <= 30 && xg < g.nx && yg < g.ny && zg < g.nz;
+      const bool valid = lane >= 1 && lane <= 30 && xg < g.nx && yg < g.ny && zg < g.z_hi;
       if (!FINAL) {
         if (valid) {
           const long long o = b * batch_g + ((long long)(zg + 1) * g.py + (yg + 1)) * g.px + (xg + 1);
@@ -360,7 +360,7 @@ void launch_one(const float4* in, float4* out, float* p_net, const float* wB, co
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  const int ntz = (g.nz + T::TZ - 1) / T::TZ;
+  const int ntz = (g.z_hi - g.z_lo + T::TZ - 1) / T::TZ;       // output planes [z_lo, z_hi)
   ConvTcGeo gg = g;
   gg.ntz = ntz;
   gg.nty = (g.ny + T::TY - 1) / T::TY;
@@ -376,6 +376,8 @@ ConvTcGeo make_conv_tc_geo(int nb, int nz, int ny, int nx) {
   g.ntx = (nx + 29) / 30;
   g.nty = 0;
   g.ntz = 0;                         // depends on the arithmetic mode; set at launch
+  g.z_lo = 0;
+  g.z_hi = nz;
   g.px = (nx + 2 + 3) & ~3;
   g.py = ny + 2;
   return g;

@@ -9,6 +9,7 @@ struct ConvTcGeo {
   int nb, nz, ny, nx;
   int px, py;             // padded pitches of the channels-last activation planes (x, y)
   int ntx, nty, ntz;      // CTA tiles
+  int z_lo, z_hi;         // output planes of a launch (default: all; a z-slab computes only what its owned planes need)
 };
 
 ConvTcGeo make_conv_tc_geo(int nb, int nz, int ny, int nx);
