@@ -1573,9 +1573,9 @@ int tfl_host_sim_step(tfl_ctx* ctx, tfl_host_sim* hs, float* p, float* U, float*
 // One domain split into z-slabs over the GPUs of a node.  The reference is
 // single-GPU; this is the multi-GPU form of the same step: rank r owns the planes [z0, z1) of every
 // field plus `halo` ghost planes per interior side, every kernel works in GLOBAL coordinates
-// (tfl_set_slab), and ghost planes are refreshed by neighbour ncclSend / ncclRecv pairs straight
-// from and into the field arrays (the planes of one channel are contiguous: nothing is packed),
-// grouped into one NCCL operation per phase:
+// (tfl_set_slab), and ghost planes are refreshed by neighbour ncclSend / ncclRecv pairs one
+// message per neighbour and direction (a gather kernel packs the planes of every channel, a scatter kernel
+// unpacks them), grouped into one NCCL operation per phase:
 //     exchange U, density (halo = 2 * margin + 2)  -> advectScalar, advectVel
 //     exchange U, density (4)                      -> buoyancy / gravity on owned +- 3, vorticity confinement
 //     exchange U, p (5)                            -> wall mask + (sum, sum^2) on owned planes
@@ -1632,6 +1632,8 @@ struct tfl_slab_sim {
   tfl_state st;
   float* U1 = nullptr;
   double* sums = nullptr;
+  float* xbuf = nullptr;            // [send down | send up | recv from below | recv from above], xbuf_side floats each
+  size_t xbuf_side = 0;
   std::vector<void*> owned;
   cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   size_t bytes_sent[3] = {0, 0, 0};
@@ -1737,6 +1739,9 @@ int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32
   if (!bad) { s->owned.push_back(p); s->U1 = (float*)p; }
   bad |= cudaMalloc(&p, 2 * sizeof(double)) != cudaSuccess;
   if (!bad) { s->owned.push_back(p); s->sums = (double*)p; }
+  s->xbuf_side = (size_t)s->halo * s->plane * 4;          // the widest exchange: halo planes of 4 channels
+  bad |= cudaMalloc(&p, 4 * s->xbuf_side * sizeof(float)) != cudaSuccess;
+  if (!bad) { s->owned.push_back(p); s->xbuf = (float*)p; }
   for (auto& pr : s->ev) for (cudaEvent_t& e : pr) bad |= cudaEventCreate(&e) != cudaSuccess;
   if (bad) { tfl_slab_sim_destroy(ctx, s); return fail(ctx, "slab_sim: allocation failed"); }
   *out = s;
@@ -1784,6 +1789,35 @@ int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* s, float* p, float* U, flo
 
 namespace {
 
+// Gather / scatter of the planes one halo exchange moves: every channel of the listed fields, `cnt` floats per
+// channel and side, to / from one contiguous buffer per neighbour (one NCCL message per neighbour and direction
+// instead of one per channel: 4 p2p operations in the group instead of 16).
+struct SlabPack {
+  float* chan[8];
+  int nchan;
+  long long cnt;                    // floats per channel and side = width * ny * nx
+  long long src_lo, src_hi;         // float offset (within a channel) of the planes sent down / up
+  long long dst_lo, dst_hi;         // ... of the ghost planes filled from below / above
+  float* send_lo; float* send_hi; float* recv_lo; float* recv_hi;     // null: no neighbour on that side
+};
+template <bool UNPACK>
+__global__ void k_slab_pack(SlabPack d) {
+  const long long per_side = d.cnt * d.nchan;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * per_side; t += (long long)gridDim.x * blockDim.x) {
+    const int side = t >= per_side;
+    const long long r = t - side * per_side;
+    const int c = (int)(r / d.cnt);
+    const long long e = r - c * d.cnt;
+    if (!UNPACK) {
+      float* buf = side ? d.send_hi : d.send_lo;
+      if (buf) buf[r] = d.chan[c][(side ? d.src_hi : d.src_lo) + e];
+    } else {
+      const float* buf = side ? d.recv_hi : d.recv_lo;
+      if (buf) d.chan[c][(side ? d.dst_hi : d.dst_lo) + e] = buf[r];
+    }
+  }
+}
+
 // Refresh `width` ghost planes on both sides of the listed fields from the neighbours' owned planes.
 int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl_grid*> fields, int width, int phase) {
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][0], ctx->stream));
@@ -1791,24 +1825,38 @@ int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl
   if (s->world > 1 && width > 0 && ctx->comm) {
     if (width > s->halo) return fail(ctx, "slab exchange of %d planes exceeds the halo (%d)", width, s->halo);
     NcclApi* nc = nccl_api();
-    const size_t cnt = (size_t)width * s->plane;
+    SlabPack d;
+    d.nchan = 0;
+    for (const tfl_grid* f : fields)
+      for (int c = 0; c < f->nc && d.nchan < 8; c++) d.chan[d.nchan++] = f->data + (size_t)c * s->cells;
+    d.cnt = (long long)width * s->plane;
+    d.src_lo = (long long)s->own_lo * s->plane;
+    d.src_hi = (long long)(s->own_hi - width) * s->plane;
+    d.dst_lo = (long long)(s->own_lo - width) * s->plane;
+    d.dst_hi = (long long)s->own_hi * s->plane;
+    const size_t side = (size_t)d.cnt * d.nchan;                  // floats per message
+    if (side > s->xbuf_side) return fail(ctx, "slab exchange buffer too small");
+    const bool lo = s->rank > 0, hi = s->rank < s->world - 1;
+    d.send_lo = lo ? s->xbuf : nullptr;
+    d.send_hi = hi ? s->xbuf + s->xbuf_side : nullptr;
+    d.recv_lo = lo ? s->xbuf + 2 * s->xbuf_side : nullptr;
+    d.recv_hi = hi ? s->xbuf + 3 * s->xbuf_side : nullptr;
+    const int blocks = (int)std::min<size_t>((2 * side + 255) / 256, 148 * 8);
+    k_slab_pack<false><<<blocks, 256, 0, ctx->stream>>>(d);
     TFL_NCCL(ctx, nc->GroupStart());
-    for (const tfl_grid* f : fields) {
-      for (int c = 0; c < f->nc; c++) {
-        float* base = f->data + (size_t)c * s->cells;
-        if (s->rank > 0) {                        // lower neighbour: my first owned planes go down
-          TFL_NCCL(ctx, nc->Send(base + (size_t)s->own_lo * s->plane, cnt, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
-          TFL_NCCL(ctx, nc->Recv(base + (size_t)(s->own_lo - width) * s->plane, cnt, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
-          s->bytes_sent[phase] += cnt * 4;
-        }
-        if (s->rank < s->world - 1) {             // upper neighbour
-          TFL_NCCL(ctx, nc->Send(base + (size_t)(s->own_hi - width) * s->plane, cnt, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
-          TFL_NCCL(ctx, nc->Recv(base + (size_t)s->own_hi * s->plane, cnt, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
-          s->bytes_sent[phase] += cnt * 4;
-        }
-      }
+    if (lo) {                                       // lower neighbour: my first owned planes go down
+      TFL_NCCL(ctx, nc->Send(d.send_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+      TFL_NCCL(ctx, nc->Recv(d.recv_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+      s->bytes_sent[phase] += side * 4;
+    }
+    if (hi) {                                       // upper neighbour
+      TFL_NCCL(ctx, nc->Send(d.send_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+      TFL_NCCL(ctx, nc->Recv(d.recv_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+      s->bytes_sent[phase] += side * 4;
     }
     TFL_NCCL(ctx, nc->GroupEnd());
+    k_slab_pack<true><<<blocks, 256, 0, ctx->stream>>>(d);
+    ctx->launches += 2;
   }
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][1], ctx->stream));
   return 0;

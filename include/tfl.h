@@ -298,8 +298,8 @@ void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* sim);
 int tfl_slab_sim_layout(const tfl_slab_sim* sim, tfl_state* state_out, int32_t info[6]);
 int tfl_slab_sim_upload(tfl_ctx* ctx, tfl_slab_sim* sim, const float* p, const float* U, const float* density);
 int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* sim, float* p, float* U, float* density);
-/* One tfluids.simulate (convnet path) on this rank's slab: three neighbour halo exchanges (ncclSend / ncclRecv
- * straight from and into the field arrays, one NCCL group per phase) and one 2-double all-reduce.  Asynchronous.
+/* One tfluids.simulate (convnet path) on this rank's slab: three neighbour halo exchanges (one packed ncclSend /
+ * ncclRecv per neighbour and direction, one NCCL group per phase) and one 2-double all-reduce.  Asynchronous.
  * A trace that leaves the local slab (margin too small) raises tfl_trace_faults. */
 int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
 int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* sim, float ms[4], int64_t bytes[3]);
