@@ -451,7 +451,7 @@ def main():
         k_ms = float(np.mean([a.elapsed_time(b) for a, b in ks]))
         algo_bytes = ALGO_BYTES["advect_vel"] * n ** 3
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic([r"k_advect_vel_pass1", r"k_advect_vel_pass2"]) if n == 128 else (None, None)
+        traffic, traffic_src = ncu_traffic([r"k_advect_vel_tile"]) if n == 128 else (None, None)
 
         # ---- BASELINE config 4: 100-iteration Jacobi sweep (stencil HBM roofline) ----------
         extra = []
@@ -550,11 +550,13 @@ def main():
         "e2e": {"value": world * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": bytes_io,
                 "d2h_bytes_per_step": bytes_io},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "advectVel (k_advect_vel_pass1+pass2, maccormackOurs)",
+        "roofline": {"bound": "hbm", "kernel": "advectVel operator, maccormackOurs (k_advect_vel_tile; the timed call also launches the "
+                                                  "4 small flag-byte / clearance refresh kernels)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms,
-                     "limiter": "instruction issue (ncu tables under profiles/)"},
+                     "limiter": "instruction issue, not HBM: 1567 warp-instructions per 32 voxels at 72 % issue-active "
+                                "(profiles/r02_advect_tile_*)"},
         "roofline_extra": extra,
         "slab": slab,
         "cpu_baseline": cpu,

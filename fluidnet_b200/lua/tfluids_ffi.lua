@@ -74,6 +74,22 @@ int tfl_cnn_create_graph(tfl_ctx*, int is_3d, int n_layers, const int32_t* cin, 
                          const int32_t* pool, const int32_t* up, int pool_is_max, int nonlin_sigmoid,
                          const float* const* weights, const float* const* biases, tfl_cnn** out);
 int tfl_simulate_step(tfl_ctx*, const tfl_state*, const tfl_mconf*, tfl_cnn*);
+typedef struct tfl_step_graph tfl_step_graph;
+typedef struct tfl_slab_sim tfl_slab_sim;
+int tfl_set_stream(tfl_ctx* ctx, void* cuda_stream);
+int tfl_step_graph_create(tfl_ctx*, const tfl_state* state, const tfl_mconf* mconf, tfl_cnn* cnn, tfl_step_graph** out);
+int tfl_step_graph_launch(tfl_ctx*, tfl_step_graph* graph);
+void tfl_step_graph_destroy(tfl_ctx*, tfl_step_graph* graph);
+int tfl_comm_unique_id(tfl_ctx*, char* id_out);
+int tfl_comm_init(tfl_ctx*, const char* id_bytes, int32_t rank, int32_t world);
+int tfl_comm_destroy(tfl_ctx*);
+int tfl_slab_sim_create(tfl_ctx*, int32_t gnz, int32_t ny, int32_t nx, int32_t margin, const float* flags,
+                        const float* U_bc, const float* U_bc_inv_mask, const float* density_bc,
+                        const float* density_bc_inv_mask, tfl_slab_sim** out);
+void tfl_slab_sim_destroy(tfl_ctx*, tfl_slab_sim* sim);
+int tfl_slab_sim_upload(tfl_ctx*, tfl_slab_sim* sim, const float* p, const float* U, const float* density);
+int tfl_slab_sim_download(tfl_ctx*, tfl_slab_sim* sim, float* p, float* U, float* density);
+int tfl_slab_sim_step(tfl_ctx*, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
 ]]
 
 local lib = ffi.load('tfl')          -- libtfl.so on the library path
@@ -271,6 +287,30 @@ function tfluids.simulateStep(mconf, batch, model)
                                    mconf.maxIter or 0, mconf.normalizeInputThreshold or 1e-5})
   check(lib.tfl_simulate_step(ctx, st, mc, model))
 end
+
+-- ---- beyond the reference: the step as a CUDA graph, and one domain in z-slabs over the GPUs of a node --------
+-- (one LuaJIT process per GPU; `id` is the 128-byte NCCL id of rank 0, moved between the processes by the host
+-- application: a file, a socket, MPI ...)
+function tfluids.captureStep(cstate, cmconf, model)          -- after one tfluids.simulateStep on a non-default stream
+  local g = ffi.new('tfl_step_graph*[1]')
+  check(lib.tfl_step_graph_create(ctx, cstate, cmconf, model, g))
+  return g[0]
+end
+function tfluids.launchStep(graph) check(lib.tfl_step_graph_launch(ctx, graph)) end
+function tfluids.commUniqueId()
+  local id = ffi.new('char[128]')
+  check(lib.tfl_comm_unique_id(ctx, id))
+  return ffi.string(id, 128)
+end
+function tfluids.commInit(id, rank, world) check(lib.tfl_comm_init(ctx, id, rank, world)) end
+function tfluids.slabCreate(gnz, ny, nx, margin, flagsHost, UBC, UBCInvMask, densityBC, densityBCInvMask)
+  local sim = ffi.new('tfl_slab_sim*[1]')
+  check(lib.tfl_slab_sim_create(ctx, gnz, ny, nx, margin or 2, flagsHost, UBC, UBCInvMask, densityBC, densityBCInvMask, sim))
+  return sim[0]
+end
+function tfluids.slabUpload(sim, p, U, density) check(lib.tfl_slab_sim_upload(ctx, sim, p, U, density)) end
+function tfluids.slabStep(sim, cmconf, model) check(lib.tfl_slab_sim_step(ctx, sim, cmconf, model)) end
+function tfluids.slabDownload(sim, p, U, density) check(lib.tfl_slab_sim_download(ctx, sim, p, U, density)) end
 
 function tfluids.synchronize() check(lib.tfl_sync(ctx)) end
 
