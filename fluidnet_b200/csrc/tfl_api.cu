@@ -54,6 +54,7 @@ struct tfl_ctx {
     size_t cells = 0;
     int nb = 0, nz = 0, ny = 0, nx = 0;
     int* changed = nullptr;                 // device word
+    const float* fresh_for = nullptr;       // set inside a slab step: the cache already mirrors these flags
   } fcache;
   // advectVel over shared-memory tiles (tfl_advect_tile.cu): the kernel reports the longest trace of a call
   // into a device word that is copied, asynchronously, into a pinned host word; the NEXT calls pick the tile
@@ -68,6 +69,7 @@ struct tfl_ctx {
   // z-slab decomposition over several GPUs (tfl_comm_init / tfl_slab_sim_*): the communicator lives here
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  bool in_slab_step = false;
 };
 
 struct tfl_cnn {
@@ -249,12 +251,19 @@ int flag_cache_ensure(tfl_ctx* ctx, const Geo& g) {
 // Byte flags + clearance field of `flags` for this call, through the context's cache: the bytes are
 // re-derived and compared on the device, the clearance is rebuilt only when one differs.
 int prepare_flags(tfl_ctx* ctx, const float* flags, const Geo& g, unsigned char** fl8, unsigned char** clear) {
-  if (flag_cache_ensure(ctx, g)) return 1;
   const size_t cells = (size_t)g.n * g.nb;
+  auto& fc = ctx->fcache;
+  if (fc.fresh_for == flags && fc.bytes && fc.cells == cells && fc.nz == g.nz && fc.ny == g.ny && fc.nx == g.nx) {
+    *fl8 = fc.bytes;                        // refreshed earlier in this (slab) step: nothing wrote the flags since
+    *clear = fc.bytes + cells;
+    return 0;
+  }
+  if (flag_cache_ensure(ctx, g)) return 1;
   *fl8 = ctx->fcache.bytes;
   *clear = ctx->fcache.bytes + cells;
   launch_flags_to_u8(flags, *fl8, (long long)cells, ctx->fcache.changed, ctx->stream);
   ctx->launches += 1 + launch_clearance(*fl8, *clear, *clear + cells, g, ctx->fcache.changed, ctx->stream);
+  if (ctx->in_slab_step) fc.fresh_for = flags;
   return 0;
 }
 
@@ -911,6 +920,16 @@ int tfl_apply_bc(tfl_ctx* ctx, const tfl_grid* x, const tfl_grid* inv_mask, cons
   if (!x || !inv_mask || !bc || !x->data || !inv_mask->data || !bc->data) return fail(ctx, "applyBC: nil tensor");
   if (!same_spatial(x, inv_mask) || !same_spatial(x, bc) || x->nc != inv_mask->nc || x->nc != bc->nc)
     return fail(ctx, "Size mismatch");
+  if (ctx->slab) {                // the planes this rank computes; ghost planes come from the neighbours
+    if (ctx->zlo < 0 || ctx->zhi > x->nz || ctx->zlo >= ctx->zhi) return fail(ctx, "applyBC: slab range does not fit");
+    const long long plane = (long long)x->ny * x->nx, cnt = (long long)(ctx->zhi - ctx->zlo) * plane;
+    for (int bc_i = 0; bc_i < x->nb * x->nc; bc_i++) {
+      const long long off = ((long long)bc_i * x->nz + ctx->zlo) * plane;
+      launch_apply_bc(x->data + off, inv_mask->data + off, bc->data + off, cnt, ctx->stream);
+    }
+    ctx->launches += x->nb * x->nc;
+    return check_launch(ctx, "applyBC");
+  }
   const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
   launch_apply_bc(x->data, inv_mask->data, bc->data, n, ctx->stream);
   ctx->launches += 1;
@@ -921,6 +940,14 @@ int tfl_clamp(tfl_ctx* ctx, const tfl_grid* x, float lo, float hi) {
   DeviceGuard guard_(ctx);
   NvtxRange range_(__func__);
   if (!x || !x->data) return fail(ctx, "clamp: nil tensor");
+  if (ctx->slab) {
+    if (ctx->zlo < 0 || ctx->zhi > x->nz || ctx->zlo >= ctx->zhi) return fail(ctx, "clamp: slab range does not fit");
+    const long long plane = (long long)x->ny * x->nx, cnt = (long long)(ctx->zhi - ctx->zlo) * plane;
+    for (int bc_i = 0; bc_i < x->nb * x->nc; bc_i++)
+      launch_clamp(x->data + ((long long)bc_i * x->nz + ctx->zlo) * plane, lo, hi, cnt, ctx->stream);
+    ctx->launches += x->nb * x->nc;
+    return check_launch(ctx, "clamp");
+  }
   const long long n = (long long)x->nb * x->nc * x->nz * x->ny * x->nx;
   launch_clamp(x->data, lo, hi, n, ctx->stream);
   ctx->launches += 1;
@@ -1882,7 +1909,13 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
   if (mc->sim_method != TFL_SIM_CONVNET) return fail(ctx, "slab_sim_step: only simMethod 'convnet' is decomposed");
   if (s->world != ctx->comm_world || s->rank != ctx->comm_rank) return fail(ctx, "slab_sim_step: communicator changed");
   const tfl_state& st = s->st;
-  auto bcs = [&]() -> int {
+  struct StepMark {                     // the flags are refreshed once per step (the two advections share them)
+    tfl_ctx* c;
+    explicit StepMark(tfl_ctx* cc) : c(cc) { c->in_slab_step = true; c->fcache.fresh_for = nullptr; }
+    ~StepMark() { c->in_slab_step = false; c->fcache.fresh_for = nullptr; }
+  } mark_(ctx);
+  auto bcs = [&]() -> int {           // on the owned planes: ghost planes are always refreshed from their owners
+    SlabScope scope(ctx, s, s->own_lo, s->own_hi);
     if (st.U_bc.data && tfl_apply_bc(ctx, &st.U, &st.U_bc_inv_mask, &st.U_bc)) return 1;
     if (st.density_bc.data && tfl_apply_bc(ctx, &st.density, &st.density_bc_inv_mask, &st.density_bc)) return 1;
     return 0;
@@ -1931,6 +1964,7 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
     if (tfl_cnn_project_from_sums(ctx, cnn, &st.p, &u1, &st.flags, s->sums, &st.p, &st.U, mc->normalize_input_threshold)) return 1;
   }
   if (bcs()) return 1;
+  SlabScope scope(ctx, s, s->own_lo, s->own_hi);
   return tfl_clamp(ctx, &st.U, -1e6f, 1e6f);
 }
 

@@ -18,6 +18,7 @@ There is no data-path collective other than those neighbour exchanges and the 2-
 A line trace or stencil that leaves the local slab (halo too small for the velocity) increments
 the library's fault counter instead of reading out of bounds; `SlabSimulator.check()` raises.
 """
+import contextlib
 import ctypes as C
 
 import torch
@@ -96,6 +97,7 @@ class SlabSimulator:
         self.mconf = dict(mconf)
         assert (self.mconf.get("simMethod") or "convnet") == "convnet"
         gnz = batch["flags"].shape[2]
+        assert margin >= 2, "margin < 2 makes the halo narrower than the widest fixed exchange (5 planes)"
         self.dec = SlabDecomposition(gnz, self.rank, self.world, halo=2 * margin + 2)
         self.margin = margin
         self.device = torch.device(device)
@@ -107,13 +109,16 @@ class SlabSimulator:
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.device)
 
     # -- helpers ---------------------------------------------------------------------------
-    def _slab_on(self):
+    @contextlib.contextmanager
+    def _slab(self, z_lo, z_hi):
+        """Slab placement of the (shared, per-device) context for the enclosed calls only."""
         d = self.dec
-        self.ctx.set_slab(d.zoff, d.gnz, d.own_lo, d.own_hi)
-        self.ctx.check(self.ctx.lib.tfl_set_slab_margin(self.ctx.h, self.margin))
-
-    def _slab_off(self):
-        self.ctx.clear_slab()
+        self.ctx.set_slab(d.zoff, d.gnz, z_lo, z_hi)
+        try:
+            self.ctx.check(self.ctx.lib.tfl_set_slab_margin(self.ctx.h, self.margin))
+            yield
+        finally:
+            self.ctx.clear_slab()
 
     def _bc(self):
         t, s = self.tfluids, self.s
@@ -138,42 +143,38 @@ class SlabSimulator:
         p, U, flags, rho = s["pDiv"], s["UDiv"], s["flags"], s["density"]
         method, strength = m.get("advectionMethod"), m.get("maccormackStrength")
         yield ("halo", [U, rho], d.halo)
-        self._slab_on()
-        t.advectScalar(m["dt"], rho, U, flags, method, None, False, strength)
-        t.advectVel(m["dt"], U, flags, method, None, strength)
-        self._slab_off()
+        with self._slab(d.own_lo, d.own_hi):
+            t.advectScalar(m["dt"], rho, U, flags, method, None, False, strength)
+            t.advectVel(m["dt"], U, flags, method, None, strength)
         self._bc()
         yield ("halo", [U, rho], 4)
-        # Buoyancy is point-wise in U but vorticity confinement then reads U three planes across the
-        # cut: apply the buoyancy on those ghost planes too (it needs density one plane further).
-        ext_lo = d.own_lo - min(3, d.lo_halo)
-        ext_hi = d.own_hi + min(3, d.hi_halo)
-        self.ctx.set_slab(d.zoff, d.gnz, ext_lo, ext_hi)
+        # Buoyancy / gravity are point-wise in U but vorticity confinement then reads U three planes across
+        # the cut: apply them on those ghost planes too (buoyancy needs density one plane further).
         dx = 1.0 / max(d.gnz, flags.size(3), flags.size(4))
-        if m.get("buoyancyScale", 0) > 0:
-            k = torch.tensor(-(dx / 4) * m["buoyancyScale"], dtype=torch.float32).item()
-            g = m.get("gravity") or [0.0, 1.0, 0.0]
-            gv = [torch.tensor(float(v), dtype=torch.float32).item() * k for v in g]
-            gv = [torch.tensor(v, dtype=torch.float32).item() for v in gv]
-            t.addBuoyancy(U, flags, rho, gv, m["dt"])
-        self._slab_on()
-        if m.get("vorticityConfinementAmp", 0) > 0:
-            t.vorticityConfinement(U, flags, dx * m["vorticityConfinementAmp"])
-        self._slab_off()
+        f32 = lambda v: torch.tensor(float(v), dtype=torch.float32).item()
+        g = m.get("gravity") or [0.0, 1.0, 0.0]
+        with self._slab(d.own_lo - min(3, d.lo_halo), d.own_hi + min(3, d.hi_halo)):
+            if (m.get("buoyancyScale") or 0) > 0:
+                k = f32(-(dx / 4) * m["buoyancyScale"])
+                t.addBuoyancy(U, flags, rho, [f32(f32(v) * k) for v in g], m["dt"])
+            if (m.get("gravityScale") or 0) > 0:                      # lib/simulate.lua:229-233
+                k = f32((-dx / 4) * m["gravityScale"])
+                t.addGravity(U, flags, [f32(f32(v) * k) for v in g], m["dt"])
+        if (m.get("vorticityConfinementAmp") or 0) > 0:
+            with self._slab(d.own_lo, d.own_hi):
+                t.vorticityConfinement(U, flags, dx * m["vorticityConfinementAmp"])
         self._bc()
         yield ("halo", [U, p], 5)
-        self._slab_on()
         c, lib = self.ctx, self.ctx.lib
-        c.use_current_stream()
-        c.check(lib.tfl_cnn_stats(c.h, t._grid(U), t._grid(flags), t._grid(self.U1), C.c_void_p(self.sums.data_ptr())))
-        self._slab_off()
+        with self._slab(d.own_lo, d.own_hi):
+            c.use_current_stream()
+            c.check(lib.tfl_cnn_stats(c.h, t._grid(U), t._grid(flags), t._grid(self.U1), C.c_void_p(self.sums.data_ptr())))
         yield ("sum", self.sums)
-        self._slab_on()
-        c.use_current_stream()
-        c.check(lib.tfl_cnn_project_from_sums(c.h, self.model.h, t._grid(p), t._grid(self.U1), t._grid(flags),
-                                              C.c_void_p(self.sums.data_ptr()), t._grid(p), t._grid(U),
-                                              float(self.model.threshold)))
-        self._slab_off()
+        with self._slab(d.own_lo, d.own_hi):
+            c.use_current_stream()
+            c.check(lib.tfl_cnn_project_from_sums(c.h, self.model.h, t._grid(p), t._grid(self.U1), t._grid(flags),
+                                                  C.c_void_p(self.sums.data_ptr()), t._grid(p), t._grid(U),
+                                                  float(self.model.threshold)))
         self._bc()
         t.clamp(U, -1e6, 1e6)
 
