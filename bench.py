@@ -243,6 +243,9 @@ def measure_slab(n, steps, warmup, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(ex, op=dist.ReduceOp.MAX)
     sim.check()
+    transport = {"nccl": "one packed ncclSend / ncclRecv per neighbour and direction, grouped per phase"}.get(
+        sim.halo_transport, "push / pull kernels over peer memory (CUDA IPC handles, remote stores over NVLink, "
+                            "system-scope step counters)") if world > 1 else "none (single rank)"
     sim.close()
     if rank != 0:
         return None
@@ -254,9 +257,8 @@ def measure_slab(n, steps, warmup, world, rank, local):
     return {"metric": "sim steps/sec on ONE %d^3 MAC grid (CNN proj), z-slab decomposed" % n, "value": 1000.0 / ms,
             "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "scaling": "strong", "grid": [n, n, n],
-            "parallelism": "z-slab x%d; per step 3 neighbour halo exchanges (one packed ncclSend/ncclRecv per neighbour "
-                           "and direction, grouped per phase) + one 2-double ncclAllReduce, all issued by libtfl "
-                           "(tfl_slab_sim_step)" % world,
+            "parallelism": "z-slab x%d; per step 3 neighbour halo exchanges + one 2-double ncclAllReduce, all issued by "
+                           "libtfl (tfl_slab_sim_step); halo transport: %s" % (world, transport),
             "halo_bytes_sent_per_rank_step": int(sum(ex_bytes)),
             "exchange_ms_last_step_max_over_ranks": {"halo_advect": ex[0], "halo_forces": ex[1],
                                                      "halo_projection": ex[2], "allreduce": ex[3]},

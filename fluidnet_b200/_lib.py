@@ -46,9 +46,10 @@ SYMBOLS = [
     "tfl_step_graph_create", "tfl_step_graph_launch", "tfl_step_graph_destroy",
     "tfl_comm_unique_id", "tfl_comm_init", "tfl_comm_destroy", "tfl_slab_sim_create", "tfl_slab_sim_destroy",
     "tfl_slab_sim_layout", "tfl_slab_sim_upload", "tfl_slab_sim_download", "tfl_slab_sim_step",
-    "tfl_slab_sim_exchange_stats",
+    "tfl_slab_sim_exchange_stats", "tfl_slab_sim_ipc_export", "tfl_slab_sim_ipc_connect",
 ]
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -137,6 +138,8 @@ def load():
     lib.tfl_slab_sim_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tfl_slab_sim_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tfl_slab_sim_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MConf), C.c_void_p]
+    lib.tfl_slab_sim_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+    lib.tfl_slab_sim_ipc_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p]
     lib.tfl_slab_sim_exchange_stats.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.tfl_alloc_host.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.tfl_free_host.argtypes = [C.c_void_p, C.c_void_p]

@@ -1661,6 +1661,14 @@ struct tfl_slab_sim {
   double* sums = nullptr;
   float* xbuf = nullptr;            // [send down | send up | recv from below | recv from above], xbuf_side floats each
   size_t xbuf_side = 0;
+  // Peer-memory halo exchange (CUDA IPC over NVLink, tfl_slab_sim_ipc_*): this rank's inbox -- per phase and side a
+  // receive buffer of xbuf_side floats that the neighbour's push kernel fills with remote stores, and a step counter
+  // it raises afterwards -- and the neighbours' inboxes mapped into this process.
+  float* inbox = nullptr;           // cudaMalloc'ed, exported: [3 phases][2 sides][xbuf_side] floats, then 64 counters
+  float* peer_inbox[2] = {nullptr, nullptr};   // lower / upper neighbour's inbox (cudaIpcOpenMemHandle)
+  unsigned int* push_done = nullptr;           // CTAs of the running push kernel that finished their stores
+  bool peer_ok = false;
+  unsigned int step_no = 0;
   std::vector<void*> owned;
   cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   size_t bytes_sent[3] = {0, 0, 0};
@@ -1712,6 +1720,7 @@ void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* s) {
   NvtxRange range_(__func__);
   if (!s) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (float* q : s->peer_inbox) if (q) cudaIpcCloseMemHandle(q);
   for (void* p : s->owned) cudaFree(p);
   for (auto& pr : s->ev) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
   delete s;
@@ -1769,6 +1778,13 @@ int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32
   s->xbuf_side = (size_t)s->halo * s->plane * 4;          // the widest exchange: halo planes of 4 channels
   bad |= cudaMalloc(&p, 4 * s->xbuf_side * sizeof(float)) != cudaSuccess;
   if (!bad) { s->owned.push_back(p); s->xbuf = (float*)p; }
+  if (s->world > 1) {
+    const size_t inbox_bytes = (6 * s->xbuf_side + 64) * sizeof(float);
+    bad |= cudaMalloc(&p, inbox_bytes) != cudaSuccess;
+    if (!bad) { s->owned.push_back(p); s->inbox = (float*)p; bad |= cudaMemset(p, 0, inbox_bytes) != cudaSuccess; }
+    bad |= cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess;
+    if (!bad) { s->owned.push_back(p); s->push_done = (unsigned int*)p; bad |= cudaMemset(p, 0, sizeof(unsigned int)) != cudaSuccess; }
+  }
   for (auto& pr : s->ev) for (cudaEvent_t& e : pr) bad |= cudaEventCreate(&e) != cudaSuccess;
   if (bad) { tfl_slab_sim_destroy(ctx, s); return fail(ctx, "slab_sim: allocation failed"); }
   *out = s;
@@ -1845,13 +1861,73 @@ __global__ void k_slab_pack(SlabPack d) {
   }
 }
 
+// Peer-memory exchange, sending half: every channel's boundary planes are written straight into the neighbours'
+// inboxes (remote stores over NVLink), and when the last CTA has finished, the step number is stored (system
+// scope, after a system-wide fence) into the neighbours' counters.
+__global__ void k_slab_push(SlabPack d, float* peer_lo_buf, float* peer_hi_buf, unsigned int* peer_lo_flag,
+                            unsigned int* peer_hi_flag, unsigned int step, unsigned int* done) {
+  const long long per_side = d.cnt * d.nchan;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * per_side; t += (long long)gridDim.x * blockDim.x) {
+    const int side = t >= per_side;
+    const long long r = t - side * per_side;
+    const int c = (int)(r / d.cnt);
+    const long long e = r - c * d.cnt;
+    float* buf = side ? peer_hi_buf : peer_lo_buf;
+    if (buf) buf[r] = d.chan[c][(side ? d.src_hi : d.src_lo) + e];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {               // every CTA's stores are fenced: publish
+      *done = 0u;
+      __threadfence_system();
+      if (peer_lo_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_lo_flag), "r"(step) : "memory");
+      if (peer_hi_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_hi_flag), "r"(step) : "memory");
+    }
+  }
+}
+// ... receiving half: wait until the neighbours' counters have reached this step, then scatter the inbox into the
+// ghost planes.  The wait is bounded (a neighbour that never arrives raises the fault counter instead of hanging
+// the GPU).
+__global__ void k_slab_pull(SlabPack d, const float* buf_lo, const float* buf_hi, const unsigned int* flag_lo,
+                            const unsigned int* flag_hi, unsigned int step, unsigned long long* faults) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    ok = 1;
+    const long long t0 = clock64();
+    for (int sde = 0; sde < 2; sde++) {
+      const unsigned int* f = sde ? flag_hi : flag_lo;
+      if (!f) continue;
+      for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - step) >= 0) break;
+        if (clock64() - t0 > 4000000000LL) { ok = 0; break; }       // ~2 s
+        __nanosleep(200);
+      }
+    }
+    if (!ok && blockIdx.x == 0 && faults) atomicAdd(faults, 1ULL);
+  }
+  __syncthreads();
+  if (!ok) return;
+  const long long per_side = d.cnt * d.nchan;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * per_side; t += (long long)gridDim.x * blockDim.x) {
+    const int side = t >= per_side;
+    const long long r = t - side * per_side;
+    const int c = (int)(r / d.cnt);
+    const long long e = r - c * d.cnt;
+    const float* buf = side ? buf_hi : buf_lo;
+    if (buf) d.chan[c][(side ? d.dst_hi : d.dst_lo) + e] = __ldcg(buf + r);
+  }
+}
+
 // Refresh `width` ghost planes on both sides of the listed fields from the neighbours' owned planes.
 int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl_grid*> fields, int width, int phase) {
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][0], ctx->stream));
   s->bytes_sent[phase] = 0;
-  if (s->world > 1 && width > 0 && ctx->comm) {
+  if (s->world > 1 && width > 0 && (ctx->comm || s->peer_ok)) {
     if (width > s->halo) return fail(ctx, "slab exchange of %d planes exceeds the halo (%d)", width, s->halo);
-    NcclApi* nc = nccl_api();
     SlabPack d;
     d.nchan = 0;
     for (const tfl_grid* f : fields)
@@ -1864,26 +1940,43 @@ int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl
     const size_t side = (size_t)d.cnt * d.nchan;                  // floats per message
     if (side > s->xbuf_side) return fail(ctx, "slab exchange buffer too small");
     const bool lo = s->rank > 0, hi = s->rank < s->world - 1;
-    d.send_lo = lo ? s->xbuf : nullptr;
-    d.send_hi = hi ? s->xbuf + s->xbuf_side : nullptr;
-    d.recv_lo = lo ? s->xbuf + 2 * s->xbuf_side : nullptr;
-    d.recv_hi = hi ? s->xbuf + 3 * s->xbuf_side : nullptr;
-    const int blocks = (int)std::min<size_t>((2 * side + 255) / 256, 148 * 8);
-    k_slab_pack<false><<<blocks, 256, 0, ctx->stream>>>(d);
-    TFL_NCCL(ctx, nc->GroupStart());
-    if (lo) {                                       // lower neighbour: my first owned planes go down
-      TFL_NCCL(ctx, nc->Send(d.send_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
-      TFL_NCCL(ctx, nc->Recv(d.recv_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
-      s->bytes_sent[phase] += side * 4;
+    const int blocks = (int)std::min<size_t>((2 * side + 255) / 256, 148 * 4);
+    if (s->peer_ok) {
+      // inbox layout: buffer (phase, from-below = 0 / from-above = 1) at ((phase * 2 + from) * xbuf_side), counters behind
+      auto buf = [&](float* base, int from) { return base + ((size_t)phase * 2 + from) * s->xbuf_side; };
+      auto flag = [&](float* base, int from) { return (unsigned int*)(base + 6 * s->xbuf_side) + phase * 2 + from; };
+      d.send_lo = d.send_hi = d.recv_lo = d.recv_hi = nullptr;
+      // my first owned planes land in the lower neighbour's "from above" slot, my last ones in the upper neighbour's "from below"
+      k_slab_push<<<blocks, 256, 0, ctx->stream>>>(d, lo ? buf(s->peer_inbox[0], 1) : nullptr, hi ? buf(s->peer_inbox[1], 0) : nullptr,
+                                                   lo ? flag(s->peer_inbox[0], 1) : nullptr, hi ? flag(s->peer_inbox[1], 0) : nullptr,
+                                                   s->step_no, s->push_done);
+      k_slab_pull<<<blocks, 256, 0, ctx->stream>>>(d, lo ? buf(s->inbox, 0) : nullptr, hi ? buf(s->inbox, 1) : nullptr,
+                                                   lo ? flag(s->inbox, 0) : nullptr, hi ? flag(s->inbox, 1) : nullptr,
+                                                   s->step_no, ctx->counters);
+      s->bytes_sent[phase] = (size_t)(lo + hi) * side * 4;
+      ctx->launches += 2;
+    } else {
+      NcclApi* nc = nccl_api();
+      d.send_lo = lo ? s->xbuf : nullptr;
+      d.send_hi = hi ? s->xbuf + s->xbuf_side : nullptr;
+      d.recv_lo = lo ? s->xbuf + 2 * s->xbuf_side : nullptr;
+      d.recv_hi = hi ? s->xbuf + 3 * s->xbuf_side : nullptr;
+      k_slab_pack<false><<<blocks, 256, 0, ctx->stream>>>(d);
+      TFL_NCCL(ctx, nc->GroupStart());
+      if (lo) {                                       // lower neighbour: my first owned planes go down
+        TFL_NCCL(ctx, nc->Send(d.send_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+        TFL_NCCL(ctx, nc->Recv(d.recv_lo, side, ncclFloat, s->rank - 1, ctx->comm, ctx->stream));
+        s->bytes_sent[phase] += side * 4;
+      }
+      if (hi) {                                       // upper neighbour
+        TFL_NCCL(ctx, nc->Send(d.send_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+        TFL_NCCL(ctx, nc->Recv(d.recv_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
+        s->bytes_sent[phase] += side * 4;
+      }
+      TFL_NCCL(ctx, nc->GroupEnd());
+      k_slab_pack<true><<<blocks, 256, 0, ctx->stream>>>(d);
+      ctx->launches += 2;
     }
-    if (hi) {                                       // upper neighbour
-      TFL_NCCL(ctx, nc->Send(d.send_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
-      TFL_NCCL(ctx, nc->Recv(d.recv_hi, side, ncclFloat, s->rank + 1, ctx->comm, ctx->stream));
-      s->bytes_sent[phase] += side * 4;
-    }
-    TFL_NCCL(ctx, nc->GroupEnd());
-    k_slab_pack<true><<<blocks, 256, 0, ctx->stream>>>(d);
-    ctx->launches += 2;
   }
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][1], ctx->stream));
   return 0;
@@ -1909,6 +2002,7 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
   if (mc->sim_method != TFL_SIM_CONVNET) return fail(ctx, "slab_sim_step: only simMethod 'convnet' is decomposed");
   if (s->world != ctx->comm_world || s->rank != ctx->comm_rank) return fail(ctx, "slab_sim_step: communicator changed");
   const tfl_state& st = s->st;
+  s->step_no += 1;                      // what the peers' counters must reach in this step's exchanges
   struct StepMark {                     // the flags are refreshed once per step (the two advections share them)
     tfl_ctx* c;
     explicit StepMark(tfl_ctx* cc) : c(cc) { c->in_slab_step = true; c->fcache.fresh_for = nullptr; }
@@ -1966,6 +2060,53 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
   if (bcs()) return 1;
   SlabScope scope(ctx, s, s->own_lo, s->own_hi);
   return tfl_clamp(ctx, &st.U, -1e6f, 1e6f);
+}
+
+// Peer-memory halos: export this rank's inbox (64-byte CUDA IPC handle) ...
+int tfl_slab_sim_ipc_export(tfl_ctx* ctx, tfl_slab_sim* s, char* handle_out) {
+  DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
+  if (!s || !handle_out) return fail(ctx, "slab_sim_ipc_export: nil argument");
+  if (!s->inbox) return fail(ctx, "slab_sim_ipc_export: a single rank has no neighbours");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= TFL_IPC_HANDLE_BYTES, "IPC handle fits the ABI buffer");
+  cudaIpcMemHandle_t h;
+  TFL_CUDA(ctx, cudaIpcGetMemHandle(&h, s->inbox));
+  memset(handle_out, 0, TFL_IPC_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+// ... and map the neighbours' (rank - 1: lo_handle, rank + 1: hi_handle; NULL where there is none).  From then on
+// tfl_slab_sim_step exchanges halos with push / pull kernels over NVLink instead of NCCL send / recv.  Every rank
+// must connect before any rank steps (the host application's barrier).
+int tfl_slab_sim_ipc_connect(tfl_ctx* ctx, tfl_slab_sim* s, const char* lo_handle, const char* hi_handle) {
+  DeviceGuard guard_(ctx);
+  NvtxRange range_(__func__);
+  if (!s || !s->inbox) return fail(ctx, "slab_sim_ipc_connect: nil argument");
+  if (!lo_handle && !hi_handle) {                 // back to NCCL (e.g. another rank could not map its neighbours)
+    TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (float*& m : s->peer_inbox) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    s->peer_ok = false;
+    return 0;
+  }
+  const char* hs[2] = {lo_handle, hi_handle};
+  const bool need[2] = {s->rank > 0, s->rank < s->world - 1};
+  for (int i = 0; i < 2; i++) {
+    if (!need[i]) continue;
+    if (!hs[i]) return fail(ctx, "slab_sim_ipc_connect: missing neighbour handle");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs[i], sizeof(h));
+    void* q = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (float*& m : s->peer_inbox) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+      return fail(ctx, "slab_sim_ipc_connect: cudaIpcOpenMemHandle: %s (halos stay on NCCL)", cudaGetErrorString(e));
+    }
+    s->peer_inbox[i] = (float*)q;
+  }
+  s->peer_ok = true;
+  return 0;
 }
 
 // Device time of the last step's three halo exchanges and of its all-reduce (ms) and the bytes this rank sent in

@@ -212,7 +212,8 @@ class NativeSlabSimulator:
     This is what a LuaJIT host would drive; torch.distributed is used here only to hand rank 0's NCCL id to the
     other ranks (any transport would do) and, in `gather`, by the tests."""
 
-    def __init__(self, batch, mconf, model_layers, device, rank=None, world=None, margin=2, group=None):
+    def __init__(self, batch, mconf, model_layers, device, rank=None, world=None, margin=2, group=None,
+                 peer_halos=True):
         import numpy as np
         from . import tfluids, model as fmodel, simulate, _lib
         self.group = group
@@ -251,6 +252,25 @@ class NativeSlabSimulator:
         info = (C.c_int32 * 6)()
         lib.tfl_slab_sim_layout(self.h, None, info)
         self.zoff, self.nz, self.own_lo, self.own_hi, self.z0, self.z1 = list(info)
+        # Halos over peer memory (CUDA IPC + NVLink) when every rank can map its neighbours; otherwise NCCL.
+        self.halo_transport = "nccl"
+        if self.world > 1 and peer_halos:
+            buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            ok = lib.tfl_slab_sim_ipc_export(self.ctx.h, self.h, buf) == 0
+            handles = [None] * self.world
+            dist.all_gather_object(handles, buf.raw if ok else None, group=group)
+            if all(h is not None for h in handles):
+                lo = handles[self.rank - 1] if self.rank > 0 else None
+                hi = handles[self.rank + 1] if self.rank < self.world - 1 else None
+                ok = lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, lo, hi) == 0
+            else:
+                ok = False
+            flags_ok = [None] * self.world
+            dist.all_gather_object(flags_ok, bool(ok), group=group)      # also the barrier before the first step
+            if all(flags_ok):
+                self.halo_transport = "peer memory (CUDA IPC over NVLink)"
+            elif ok:                                          # every rank must use the same transport
+                self.ctx.check(lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, None, None))
 
     def step(self):
         self.ctx.use_current_stream()

@@ -57,7 +57,7 @@ def _problem(n):
     return batch, mconf, synth.make_model(True)
 
 
-def _worker(rank, world, port, n, steps, q, native=False):
+def _worker(rank, world, port, n, steps, q, native=False, peer=True):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -67,8 +67,11 @@ def _worker(rank, world, port, n, steps, q, native=False):
         from fluidnet_b200.slab import SlabSimulator, NativeSlabSimulator
         batch, mconf, mnp = _problem(n)
         tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+        kw = {"peer_halos": peer} if native else {}
         sim = (NativeSlabSimulator if native else SlabSimulator)(tb, mconf, mnp["layers"], torch.device("cuda", rank),
-                                                               rank, world)
+                                                               rank, world, **kw)
+        if native and peer:
+            assert sim.halo_transport.startswith("peer memory"), sim.halo_transport
         for _ in range(steps):
             sim.step()
         sim.check()
@@ -94,16 +97,18 @@ def _worker(rank, world, port, n, steps, q, native=False):
         raise
 
 
-@pytest.mark.parametrize("native", [False, True], ids=["torch_exchange", "library_nccl"])
+@pytest.mark.parametrize("native,peer", [(False, False), (True, False), (True, True)],
+                         ids=["torch_exchange", "library_nccl", "library_peer_memory"])
 @pytest.mark.parametrize("world,n,steps", [(2, 48, 2), (4, 64, 2)])
-def test_multi_gpu_slab_matches_single_gpu(world, n, steps, native):
-    """native: the whole decomposed step inside libtfl.so (tfl_slab_sim_step, NCCL owned by the context)."""
+def test_multi_gpu_slab_matches_single_gpu(world, n, steps, native, peer):
+    """native: the whole decomposed step inside libtfl.so (tfl_slab_sim_step, NCCL owned by the context); peer: its
+    halos through CUDA-IPC peer memory (push / pull kernels over NVLink) instead of ncclSend / ncclRecv."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, steps, q, native)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, steps, q, native, peer)) for r in range(world)]
     for p in procs:
         p.start()
     res = _collect(procs, q, 150)
