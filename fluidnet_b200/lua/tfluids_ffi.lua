@@ -90,6 +90,8 @@ void tfl_slab_sim_destroy(tfl_ctx*, tfl_slab_sim* sim);
 int tfl_slab_sim_upload(tfl_ctx*, tfl_slab_sim* sim, const float* p, const float* U, const float* density);
 int tfl_slab_sim_download(tfl_ctx*, tfl_slab_sim* sim, float* p, float* U, float* density);
 int tfl_slab_sim_step(tfl_ctx*, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
+int tfl_slab_sim_ipc_export(tfl_ctx*, tfl_slab_sim* sim, char* handle_out);
+int tfl_slab_sim_ipc_connect(tfl_ctx*, tfl_slab_sim* sim, const char* lo_handle, const char* hi_handle);
 ]]
 
 local lib = ffi.load('tfl')          -- libtfl.so on the library path
@@ -308,6 +310,12 @@ function tfluids.slabCreate(gnz, ny, nx, margin, flagsHost, UBC, UBCInvMask, den
   check(lib.tfl_slab_sim_create(ctx, gnz, ny, nx, margin or 2, flagsHost, UBC, UBCInvMask, densityBC, densityBCInvMask, sim))
   return sim[0]
 end
+function tfluids.slabIpcHandle(sim)                 -- 64 bytes for the neighbours (peer-memory halos, optional)
+  local h = ffi.new('char[64]')
+  check(lib.tfl_slab_sim_ipc_export(ctx, sim, h))
+  return ffi.string(h, 64)
+end
+function tfluids.slabIpcConnect(sim, loHandle, hiHandle) check(lib.tfl_slab_sim_ipc_connect(ctx, sim, loHandle, hiHandle)) end
 function tfluids.slabUpload(sim, p, U, density) check(lib.tfl_slab_sim_upload(ctx, sim, p, U, density)) end
 function tfluids.slabStep(sim, cmconf, model) check(lib.tfl_slab_sim_step(ctx, sim, cmconf, model)) end
 function tfluids.slabDownload(sim, p, U, density) check(lib.tfl_slab_sim_download(ctx, sim, p, U, density)) end
