@@ -858,22 +858,30 @@ k_jacobi_march(const unsigned char* __restrict__ mask, const float* __restrict__
 // its plane-by-plane march; here a sweep is one halo round trip, ~500 instructions per thread and the barrier.
 // p is read with ld.global.cg (L1 is not coherent across CTAs).  Same per-cell expression (bit-identical).
 constexpr int kJZ = 4;
-__global__ void __launch_bounds__(256, 4)
+constexpr int kJG = 4;        // blocks per CTA: fewer, fatter CTAs make the grid-wide barrier (one atomic per CTA) cheaper
+__global__ void __launch_bounds__(256 * kJG, 1)
 k_jacobi_resident(const unsigned char* __restrict__ mask, const float* __restrict__ div, float* pa, float* pb, Geo g,
-                  int sweeps) {
+                  int sweeps, int nblocks) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   extern __shared__ float4 jsm[];
-  float4 (*rows)[kJY + 2][32] = reinterpret_cast<float4 (*)[kJY + 2][32]>(jsm);               // [kJZ][kJY + 2][32]
-  float4 (*dvs)[kJY][32] = reinterpret_cast<float4 (*)[kJY][32]>(jsm + kJZ * (kJY + 2) * 32);   // [kJZ][kJY][32]
+  // thread group threadIdx.z of the CTA owns block blockIdx.x * kJG + threadIdx.z (x tile fastest, then y, then z chunk)
+  constexpr int kGroupF4 = kJZ * (kJY + 2) * 32 + kJZ * kJY * 32;
+  float4* gsm = jsm + threadIdx.z * kGroupF4;
+  float4 (*rows)[kJY + 2][32] = reinterpret_cast<float4 (*)[kJY + 2][32]>(gsm);               // [kJZ][kJY + 2][32]
+  float4 (*dvs)[kJY][32] = reinterpret_cast<float4 (*)[kJY][32]>(gsm + kJZ * (kJY + 2) * 32);   // [kJZ][kJY][32]
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i0 = (blockIdx.x * 32 + tx) * 4;
-  const int j = blockIdx.y * kJY + ty;
+  const int blk = blockIdx.x * kJG + threadIdx.z;
+  const bool live = blk < nblocks;                         // a group without a block only takes part in the barriers
+  const int nxt = g.nx / 128, nyt = g.ny / kJY;
+  const int bx = blk % nxt, by = (blk / nxt) % nyt, bz = blk / (nxt * nyt);
+  const int i0 = (bx * 32 + tx) * 4;
+  const int j = by * kJY + ty;
   const int nchunks = (g.nz + kJZ - 1) / kJZ;
-  const int b = blockIdx.z / nchunks;
-  const int k0 = (blockIdx.z % nchunks) * kJZ;
-  const int np = min(kJZ, g.nz - k0);                      // planes of this block
+  const int b = live ? bz / nchunks : 0;
+  const int k0 = live ? (bz % nchunks) * kJZ : 0;
+  const int np = live ? min(kJZ, g.nz - k0) : 0;           // planes of this block
   const int sy = g.nx, sz = g.nx * g.ny;
-  const long long base = b * g.n + (long long)k0 * sz + (long long)j * sy + i0;
+  const long long base = live ? b * g.n + (long long)k0 * sz + (long long)j * sy + i0 : 0;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool has_left = tx == 0 && i0 > 0, has_right = tx == 31 && i0 + 4 < g.nx;
   unsigned m4[kJZ];
@@ -889,8 +897,8 @@ k_jacobi_resident(const unsigned char* __restrict__ mask, const float* __restric
     const float* prev = (s & 1) ? pb : pa;                 // sweep 0 reads pa and writes pb
     float* cur = (s & 1) ? pa : pb;
     // halo of the block, all requests in flight together
-    const float4 zlo = k0 > 0 ? __ldcg((const float4*)(prev + base - sz)) : zero4;
-    const float4 zhi = k0 + np < g.nz ? __ldcg((const float4*)(prev + base + (long long)np * sz)) : zero4;
+    const float4 zlo = (live && k0 > 0) ? __ldcg((const float4*)(prev + base - sz)) : zero4;
+    const float4 zhi = (live && k0 + np < g.nz) ? __ldcg((const float4*)(prev + base + (long long)np * sz)) : zero4;
     float left[kJZ], right[kJZ];
 #pragma unroll
     for (int k = 0; k < kJZ; k++) {
@@ -902,7 +910,7 @@ k_jacobi_resident(const unsigned char* __restrict__ mask, const float* __restric
       right[k] = (in && has_right) ? __ldcg(prev + c + 4) : 0.0f;
       rows[k][ty + 1][tx] = pc[k];
     }
-    __syncthreads();
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)threadIdx.z) : "memory");      // this group's rows are in place
     float4 below = zlo;
 #pragma unroll
     for (int k = 0; k < kJZ; k++) {
@@ -1154,7 +1162,7 @@ bool launch_jacobi_sweeps(const unsigned char* mask, const float* div, float* pa
   if (!g.is3d || !aligned || g.nx % 128 != 0 || g.ny % kJY != 0 || g.nz < 4 || g.zlo != 0 || g.zhi != g.nz ||
       g.n * g.nb > (3LL << 20) || sweeps < 2)
     return false;
-  const int smem = (kJZ * (kJY + 2) * 32 + kJZ * kJY * 32) * (int)sizeof(float4);
+  const int smem = kJG * (kJZ * (kJY + 2) * 32 + kJZ * kJY * 32) * (int)sizeof(float4);
   static int capacity = -1;          // resident CTAs of this kernel on the device
   if (capacity < 0) {
     int dev = 0, sms = 0, per_sm = 0, coop = 0;
@@ -1163,16 +1171,17 @@ bool launch_jacobi_sweeps(const unsigned char* mask, const float* div, float* pa
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     capacity = 0;
     if (coop && cudaFuncSetAttribute(k_jacobi_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_resident, 256, smem) == cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_resident, 256 * kJG, smem) == cudaSuccess)
       capacity = sms * per_sm;
     cudaGetLastError();
   }
   const int nch = (g.nz + kJZ - 1) / kJZ;
-  const long long ctas = (long long)(g.nx / 128) * (g.ny / kJY) * nch * g.nb;
+  int nblocks = (g.nx / 128) * (g.ny / kJY) * nch * g.nb;
+  const int ctas = (nblocks + kJG - 1) / kJG;
   if (ctas > capacity) return false;
-  dim3 block(32, kJY, 1), grid(g.nx / 128, g.ny / kJY, nch * g.nb);
+  dim3 block(32, kJY, kJG), grid(ctas, 1, 1);
   Geo gg = g;
-  void* args[] = {(void*)&mask, (void*)&div, (void*)&pa, (void*)&pb, (void*)&gg, (void*)&sweeps};
+  void* args[] = {(void*)&mask, (void*)&div, (void*)&pa, (void*)&pb, (void*)&gg, (void*)&sweeps, (void*)&nblocks};
   if (cudaLaunchCooperativeKernel((const void*)k_jacobi_resident, grid, block, args, smem, st) != cudaSuccess) {
     cudaGetLastError();
     return false;
