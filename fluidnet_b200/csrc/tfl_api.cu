@@ -1341,7 +1341,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   const bool has_density = s->density.data != nullptr;
   if (cnn_ensure_act(ctx, m, g)) return 1;
   if (arena_reserve(ctx, carve_bytes({cells * 4, cells * 4 * g.nc, cells * 4, cells * 4 * g.nc, cells * 4 * g.nc,
-                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells * 12})))
+                                      cells * 12, cells * 4, cells * 4, 4 * (size_t)g.nb, cells * 12, cells / 4 + 64})))
     return 1;
   Carver cv(ctx);
   float* fwd_s = cv.take<float>(cells);
@@ -1354,6 +1354,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   float* p_net = cv.take<float>(cells);
   float* scale = cv.take<float>(g.nb);
   float* force = cv.take<float>(cells * 3);
+  unsigned char* qmask_buf = cv.take<unsigned char>(cells / 4 + 64);
   cudaStream_t st = ctx->stream;
   // Byte copy of the flags for this step (every bit the kernels test is below 256) and, when a byte
   // differs from the previous step's copy, the clearance field of the advection fast path.
@@ -1361,11 +1362,24 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   if (prepare_flags(ctx, s->flags.data, g, &fl8, &clear)) return 1;
   const bool ov = ctx->ov.active;
   if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_u_in, 0));          // U has arrived from the host
+  // Which quads of the BC arrays are the identity pair (the point-wise stages then skip their loads): rebuilt
+  // every step from the arrays, beside the advection (on the side stream when there is one).
+  const unsigned char* qmask = nullptr;
+  const bool u_bc0 = s->U_bc.data && s->U_bc_inv_mask.data;
+  const bool d_bc0 = has_density && s->density_bc.data && s->density_bc_inv_mask.data;
+  bool qmask_on_side = false;
   if (has_density) {
     // Density and velocity advection are independent (both read the old U): run the density
     // kernels on a side stream so the two latency-bound kernel pairs overlap.
     TFL_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    if (launch_bc_quad_mask(u_bc0 ? s->U_bc_inv_mask.data : nullptr, u_bc0 ? s->U_bc.data : nullptr,
+                            d_bc0 ? s->density_bc_inv_mask.data : nullptr, d_bc0 ? s->density_bc.data : nullptr,
+                            qmask_buf, g, ctx->side_stream)) {
+      qmask = qmask_buf;
+      qmask_on_side = true;
+      ctx->launches += 1;
+    }
     if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_d_in, 0));
     const int nl = advect_scalar_dispatch(ctx, mc->dt, s->density.data, s->U.data, fl8, fl8, clear, mc->advection_method,
                                           0, mc->maccormack_strength, tmp_s, fwd_s, fwd_pos, g, g, ctx->side_stream);
@@ -1380,6 +1394,11 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
     ctx->launches += nl;
   }
   if (has_density) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  if (!qmask_on_side && launch_bc_quad_mask(u_bc0 ? s->U_bc_inv_mask.data : nullptr, u_bc0 ? s->U_bc.data : nullptr, nullptr,
+                                            nullptr, qmask_buf, g, st)) {
+    qmask = qmask_buf;
+    ctx->launches += 1;
+  }
   const int dmax = std::max(g.nx, std::max(g.ny, g.gnz));
   const double dx = 1.0 / (double)dmax;
   const bool u_bc = s->U_bc.data && s->U_bc_inv_mask.data;
@@ -1393,7 +1412,7 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   }
   launch_post_advect(has_density ? tmp_s : nullptr, tmp_u, fl8, has_density ? s->density.data : nullptr,
                      s->U.data, u_bc ? s->U_bc_inv_mask.data : nullptr, u_bc ? s->U_bc.data : nullptr,
-                     d_bc ? s->density_bc_inv_mask.data : nullptr, d_bc ? s->density_bc.data : nullptr, do_buoy, bs,
+                     d_bc ? s->density_bc_inv_mask.data : nullptr, d_bc ? s->density_bc.data : nullptr, qmask, do_buoy, bs,
                      g, st);
   ctx->launches += 1;
   if (ov && has_density && ctx->ov.density_host) {
@@ -1422,14 +1441,14 @@ static int simulate_step_fused(tfl_ctx* ctx, const tfl_state* s, const tfl_mconf
   double* sums = ctx->dscratch + 64;
   TFL_CUDA(ctx, cudaMemsetAsync(sums, 0, sizeof(double) * 2 * g.nb, st));
   launch_vort_bc_mask(s->U.data, fl8, force, do_vort, u_bc ? s->U_bc_inv_mask.data : nullptr,
-                      u_bc ? s->U_bc.data : nullptr, 1, sums, g, st);
+                      u_bc ? s->U_bc.data : nullptr, qmask, 1, sums, g, st);
   const ConvTcGeo& tg = m->act_geo;
   if (ov) TFL_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_p_in, 0));          // pDiv is first read here
   launch_cnn_inputs_fused(s->p.data, s->U.data, fl8, sums, mc->normalize_input_threshold, scale, m->act[0],
                           tg.px, tg.py, g, st);
   run_conv_stack(m, p_net, st);
   launch_cnn_finish_fused(p_net, s->U.data, fl8, scale, s->p.data, u_bc ? s->U_bc_inv_mask.data : nullptr,
-                          u_bc ? s->U_bc.data : nullptr, -1e6f, 1e6f, g, st);
+                          u_bc ? s->U_bc.data : nullptr, qmask, -1e6f, 1e6f, g, st);
   ctx->launches += 6;
   return check_launch(ctx, "simulate_step (fused)");
 }

@@ -25,7 +25,14 @@ namespace tfl {
 struct BcPtrs {
   const float* u_inv; const float* u_bc;        // may be null (no velocity BC)
   const float* d_inv; const float* d_bc;        // may be null (no density BC)
+  // Quad kernels only, may be null: one byte per 4 cells, bit 0 = the velocity BC of the quad is the identity pair
+  // (invMask bits == 1.0f and bc bits == +0.0f on all 4 cells of all channels), bit 1 = the same for the density
+  // BC.  Such a quad applies x * 1.0f + 0.0f without loading the arrays (k_bc_quad_mask rebuilds the bytes every
+  // step from the arrays themselves: nothing is assumed about the caller keeping them unchanged).
+  const unsigned char* qmask;
 };
+// x * 1.0f is x; x + (+0.0f) is x except that it turns -0 into +0: kept, so that skipping the loads changes nothing.
+__device__ __forceinline__ float bc_identity(float x) { return (x * 1.0f) + 0.0f; }
 
 __device__ __forceinline__ float bc_apply(float x, const float* __restrict__ inv, const float* __restrict__ bc,
                                           long long o) {
@@ -290,9 +297,16 @@ __global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ 
   const long long sb = b * g.n, ub = (long long)b * g.nc * g.n;
   float rc[4];
   zero4(rc);
+  auto quad_bits = [&](long long o) { return bc.qmask ? (int)__ldg(bc.qmask + (o >> 2)) : 0; };
+  const int qm = quad_bits(sb + c0);
   auto dens_bc = [&](long long o, float (&out)[4]) {          // BC(tmp_s) of the quad at offset o
     ld4(tmp_s + o, out);
     if (bc.d_inv) {
+      if (quad_bits(o) & 2) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) out[v] = bc_identity(out[v]);
+        return;
+      }
       float iv[4], bv[4];
       ld4(bc.d_inv + o, iv);
       ld4(bc.d_bc + o, bv);
@@ -304,15 +318,20 @@ __global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ 
     dens_bc(sb + c0, rc);
     float fin[4] = {rc[0], rc[1], rc[2], rc[3]};
     if (bc.d_inv) {        // second and third setConstVals of the step (lib/simulate.lua:252, :321)
-      float iv[4], bv[4];
-      ld4(bc.d_inv + sb + c0, iv);
-      ld4(bc.d_bc + sb + c0, bv);
+      if (qm & 2) {
 #pragma unroll
-      for (int v = 0; v < 4; v++) {
-        float t = fin[v] * iv[v];
-        t = t + bv[v];
-        t = t * iv[v];
-        fin[v] = t + bv[v];
+        for (int v = 0; v < 4; v++) fin[v] = bc_identity(bc_identity(fin[v]));
+      } else {
+        float iv[4], bv[4];
+        ld4(bc.d_inv + sb + c0, iv);
+        ld4(bc.d_bc + sb + c0, bv);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          float t = fin[v] * iv[v];
+          t = t + bv[v];
+          t = t * iv[v];
+          fin[v] = t + bv[v];
+        }
       }
     }
     st4(density + sb + c0, fin);
@@ -323,11 +342,16 @@ __global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ 
     if (a < g.nc) {
       ld4(tmp_u + ub + a * g.n + c0, u[a]);
       if (bc.u_inv) {
-        float iv[4], bv[4];
-        ld4(bc.u_inv + ub + a * g.n + c0, iv);
-        ld4(bc.u_bc + ub + a * g.n + c0, bv);
+        if (qm & 1) {
 #pragma unroll
-        for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+          for (int v = 0; v < 4; v++) u[a][v] = bc_identity(u[a][v]);
+        } else {
+          float iv[4], bv[4];
+          ld4(bc.u_inv + ub + a * g.n + c0, iv);
+          ld4(bc.u_bc + ub + a * g.n + c0, bv);
+#pragma unroll
+          for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+        }
       }
     }
   }
@@ -338,7 +362,10 @@ __global__ void __launch_bounds__(256) k_post_advect4(const float* __restrict__ 
     zero4(ry); zero4(rz);
     if (i0 > 0) {
       rl = __ldg(tmp_s + sb + c0 - 1);
-      if (bc.d_inv) { const float t = rl * __ldg(bc.d_inv + sb + c0 - 1); rl = t + __ldg(bc.d_bc + sb + c0 - 1); }
+      if (bc.d_inv) {
+        if (quad_bits(sb + c0 - 4) & 2) rl = bc_identity(rl);
+        else { const float t = rl * __ldg(bc.d_inv + sb + c0 - 1); rl = t + __ldg(bc.d_bc + sb + c0 - 1); }
+      }
     }
     if (j > 0) dens_bc(sb + c0 - sy, ry);
     if (IS3D && k > 0) dens_bc(sb + c0 - sz, rz);
@@ -399,14 +426,20 @@ __global__ void __launch_bounds__(256) k_vort_bc_mask4(float* __restrict__ U, co
       }
     }
     if (bc.u_inv) {
+      const bool identity = bc.qmask && (__ldg(bc.qmask + ((b * g.n + c0) >> 2)) & 1);
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         if (a < g.nc) {
-          float iv[4], bv[4];
-          ld4(bc.u_inv + ub + a * g.n + c0, iv);
-          ld4(bc.u_bc + ub + a * g.n + c0, bv);
+          if (identity) {
 #pragma unroll
-          for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+            for (int v = 0; v < 4; v++) u[a][v] = bc_identity(u[a][v]);
+          } else {
+            float iv[4], bv[4];
+            ld4(bc.u_inv + ub + a * g.n + c0, iv);
+            ld4(bc.u_bc + ub + a * g.n + c0, bv);
+#pragma unroll
+            for (int v = 0; v < 4; v++) { const float t = u[a][v] * iv[v]; u[a][v] = t + bv[v]; }
+          }
         }
       }
     }
@@ -529,11 +562,12 @@ __global__ void __launch_bounds__(256) k_cnn_finish_fused4(const float* __restri
 #pragma unroll
   for (int v = 0; v < 4; v++)
     wall_mask_from_flags(q.c.c[v], q.xm(v), q.xp(v), q.ym.c[v], q.yp.c[v], q.zm.c[v], q.zp.c[v], IS3D, z[v]);
+  const bool bc_identity_quad = bc.qmask && (__ldg(bc.qmask + ((b * g.n + c0) >> 2)) & 1);
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     if (a < g.nc) {
       float iv[4] = {1.0f, 1.0f, 1.0f, 1.0f}, bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (bc.u_inv) {
+      if (bc.u_inv && !bc_identity_quad) {            // an identity quad keeps iv = 1, bv = +0: same operations below
         ld4(bc.u_inv + ub + a * g.n + c0, iv);
         ld4(bc.u_bc + ub + a * g.n + c0, bv);
       }
@@ -683,6 +717,33 @@ __global__ void __launch_bounds__(256) k_vort_force4(const float* __restrict__ c
   st4(fb, fx); st4(fb + g.n, fy); st4(fb + 2 * g.n, fz);
 }
 
+// One byte per quad: which BCs are the identity pair there (see BcPtrs::qmask).
+template <bool IS3D>
+__global__ void __launch_bounds__(256) k_bc_quad_mask(const float* __restrict__ u_inv, const float* __restrict__ u_bc,
+                                                      const float* __restrict__ d_inv, const float* __restrict__ d_bc,
+                                                      unsigned char* __restrict__ qmask, Geo gin) {
+  const Geo g = static_geo<IS3D>(gin);
+  int b, k, j, i0;
+  if (!thread_cell4(g, b, k, j, i0)) return;
+  const long long o = b * g.n + cell(g, k, j, i0);
+  const long long ub = (long long)b * g.nc * g.n + cell(g, k, j, i0);
+  auto identity = [](const float* inv, const float* bcv) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(inv));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(bcv));
+    const unsigned one = 0x3f800000u;
+    return a.x == one && a.y == one && a.z == one && a.w == one && (c.x | c.y | c.z | c.w) == 0u;
+  };
+  int bits = 0;
+  if (u_inv) {
+    bool id = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) if (a < g.nc) id = id && identity(u_inv + ub + a * g.n, u_bc + ub + a * g.n);
+    bits |= id ? 1 : 0;
+  }
+  if (d_inv && identity(d_inv + o, d_bc + o)) bits |= 2;
+  qmask[o >> 2] = (unsigned char)bits;
+}
+
 // Rows the quad kernels cover: nx a multiple of 4 and a block shape that tiles 256 threads.
 static inline bool quad_dims(const Geo& g, dim3& grid, dim3& block) {
   if (g.nx % 4 != 0 || g.zlo != 0 || g.zhi != g.nz) return false;
@@ -728,10 +789,19 @@ bool launch_vort_curl_quad(const float* U, float* curl, float* cnorm, float* for
   return true;
 }
 
+// false if the quad kernels do not cover this grid (the stages then run without the mask)
+bool launch_bc_quad_mask(const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
+                         unsigned char* qmask, const Geo& g, cudaStream_t st) {
+  dim3 qg, qb;
+  if (!quad_dims(g, qg, qb) || !aligned16({u_inv, u_bc, d_inv, d_bc}) || (!u_inv && !d_inv)) return false;
+  TFL_LAUNCH4F(k_bc_quad_mask, g, qg, qb, st, u_inv, u_bc, d_inv, d_bc, qmask, g);
+  return true;
+}
+
 void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
-                        int do_buoy, const float s[3], const Geo& g, cudaStream_t st) {
-  BcPtrs bc{u_inv, u_bc, d_inv, d_bc};
+                        const unsigned char* qmask, int do_buoy, const float s[3], const Geo& g, cudaStream_t st) {
+  BcPtrs bc{u_inv, u_bc, d_inv, d_bc, qmask};
   dim3 qg, qb;
   if (quad_dims(g, qg, qb) && aligned16({tmp_s, tmp_u, flags, density, U, u_inv, u_bc, d_inv, d_bc})) {
     TFL_LAUNCH4F(k_post_advect4, g, qg, qb, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
@@ -740,9 +810,9 @@ void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned c
   TFL_LAUNCH3F(k_post_advect, g, st, tmp_s, tmp_u, flags, density, U, bc, do_buoy, s[0], s[1], s[2], g);
 }
 void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort,
-                         const float* u_inv, const float* u_bc, int mask_mode, double* sums,
+                         const float* u_inv, const float* u_bc, const unsigned char* qmask, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st) {
-  BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
+  BcPtrs bc{u_inv, u_bc, nullptr, nullptr, qmask};
   dim3 qg, qb;
   if (quad_dims(g, qg, qb) && aligned16({U, flags, force, u_inv, u_bc})) {
     TFL_LAUNCH4F(k_vort_bc_mask4, g, qg, qb, st, U, flags, force, do_vort, bc, mask_mode, sums, g);
@@ -761,9 +831,9 @@ void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned
   TFL_LAUNCH3F(k_cnn_inputs_fused, g, st, p_div, U1, flags, sums, threshold, scale_out, (float4*)x0, px, py, g);
 }
 void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* flags, const float* scale, float* p_out,
-                             const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
-                             cudaStream_t st) {
-  BcPtrs bc{u_inv, u_bc, nullptr, nullptr};
+                             const float* u_inv, const float* u_bc, const unsigned char* qmask, float lo, float hi,
+                             const Geo& g, cudaStream_t st) {
+  BcPtrs bc{u_inv, u_bc, nullptr, nullptr, qmask};
   dim3 qg, qb;
   if (quad_dims(g, qg, qb) && aligned16({p_net, U, flags, p_out, u_inv, u_bc})) {
     TFL_LAUNCH4F(k_cnn_finish_fused4, g, qg, qb, st, p_net, U, flags, scale, p_out, bc, lo, hi, g);

@@ -75,21 +75,24 @@ void launch_cnn_finish(const float* p_net, const float* U1, const float* flags, 
                        float* p_out, float* U_out, const Geo& g, cudaStream_t st);
 
 // ---- tfl_fused.cu (-fmad=false): fused point-wise stages of the convnet step ----
+// qmask (may be null): BcPtrs::qmask of tfl_fused.cu, filled by launch_bc_quad_mask for the same step.
+bool launch_bc_quad_mask(const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
+                         unsigned char* qmask, const Geo& g, cudaStream_t st);
 void launch_post_advect(const float* tmp_s, const float* tmp_u, const unsigned char* flags, float* density, float* U,
                         const float* u_inv, const float* u_bc, const float* d_inv, const float* d_bc,
-                        int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
+                        const unsigned char* qmask, int do_buoy, const float s[3], const Geo& g, cudaStream_t st);
 void launch_vort_curl(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
                       cudaStream_t st);
 bool launch_vort_curl_quad(const float* U, float* curl, float* cnorm, float* force, float strength, const Geo& g,
                            cudaStream_t st);
-void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort, const float* u_inv, const float* u_bc, int mask_mode, double* sums,
+void launch_vort_bc_mask(float* U, const unsigned char* flags, const float* force, int do_vort, const float* u_inv, const float* u_bc, const unsigned char* qmask, int mask_mode, double* sums,
                          const Geo& g, cudaStream_t st);
 void launch_cnn_inputs_fused(const float* p_div, const float* U1, const unsigned char* flags, const double* sums,
                              float threshold, float* scale_out, float* x0, int px, int py, const Geo& g,
                              cudaStream_t st);
 void launch_cnn_finish_fused(const float* p_net, float* U, const unsigned char* flags, const float* scale, float* p_out,
-                             const float* u_inv, const float* u_bc, float lo, float hi, const Geo& g,
-                             cudaStream_t st);
+                             const float* u_inv, const float* u_bc, const unsigned char* qmask, float lo, float hi,
+                             const Geo& g, cudaStream_t st);
 
 // ---- tfl_cnn.cu ----
 // Generic direct convolution (fp32 FMA): in [b][cin][z][y][x] -> out [b][cout][z][y][x].
