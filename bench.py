@@ -445,16 +445,25 @@ def main():
         reps = 10
         for _ in range(3):
             tfluids.advectVel(0.1, U, gb["flags"], "maccormackOurs", Ud, 0.6)
-        ks = []
+        # CUDA events right around the kernel's launch, on the stream it is launched on (the library records them
+        # when asked to: the operator call around it also refreshes the flag bytes, which is not this kernel)
+        lib.tfl_debug_time_advect_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.tfl_debug_last_advect_kernel_ms.argtypes = [ctypes.c_void_p]
+        lib.tfl_debug_last_advect_kernel_ms.restype = ctypes.c_float
+        lib.tfl_debug_time_advect_kernel(ctx.h, 1)
+        ks, ops = [], []
         for _ in range(reps):
             flush.fill_(0.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             tfluids.advectVel(0.1, U, gb["flags"], "maccormackOurs", Ud, 0.6)
             b.record(stream)
-            ks.append((a, b))
-        stream.synchronize()
-        k_ms = float(np.mean([a.elapsed_time(b) for a, b in ks]))
+            stream.synchronize()
+            ks.append(float(lib.tfl_debug_last_advect_kernel_ms(ctx.h)))
+            ops.append(a.elapsed_time(b))
+        lib.tfl_debug_time_advect_kernel(ctx.h, 0)
+        op_ms = float(np.mean(ops))
+        k_ms = float(np.mean(ks)) if min(ks) > 0 else op_ms
         algo_bytes = ALGO_BYTES["advect_vel"] * n ** 3
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic([r"k_advect_vel_tile"]) if n == 128 else (None, None)
@@ -561,8 +570,9 @@ def main():
         "e2e": {"value": world * e2e_steps / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": bytes_io,
                 "d2h_bytes_per_step": bytes_io},
         "gpu_launches": int(graph_launches),
-        "roofline": {"bound": "hbm", "kernel": "advectVel operator, maccormackOurs (k_advect_vel_tile; the timed call also launches the "
-                                                  "4 small flag-byte / clearance refresh kernels)",
+        "roofline": {"bound": "hbm", "kernel": "k_advect_vel_tile (advectVel, maccormackOurs): the step's longest kernel, timed "
+                                                  "alone with CUDA events around its launch",
+                     "operator_ms": op_ms,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": algo_bytes, "peak_source": peak_src, "kernel_ms": k_ms,

@@ -65,6 +65,9 @@ struct tfl_ctx {
     int mode = -1;                          // -1 automatic, 0 two-kernel version, 1 / 2 forced halo
     int variant = 0;                        // tile shape (tuning)
     int calls_since_probe = 0;
+    // bench.py's roofline: CUDA events right around the tile kernel's launch (off unless asked for)
+    bool timed = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   } tile;
   // z-slab decomposition over several GPUs (tfl_comm_init / tfl_slab_sim_*): the communicator lives here
   ncclComm_t comm = nullptr;
@@ -297,7 +300,10 @@ int advect_vel_dispatch(tfl_ctx* ctx, float dt, const float* U, const FT* flags,
     const int hf = tile_halo_choice(ctx, true);
     if (hf > 0 && tl.dev && tl.host) {
       cudaMemsetAsync(tl.dev, 0, sizeof(unsigned int), st);
-      if (launch_advect_vel_tile(dt, U, fl8, clear, strength, dst, g, hf, tl.variant, tl.dev, st)) {
+      if (tl.timed) cudaEventRecord(tl.ev0, st);
+      const bool launched = launch_advect_vel_tile(dt, U, fl8, clear, strength, dst, g, hf, tl.variant, tl.dev, st);
+      if (tl.timed) cudaEventRecord(tl.ev1, st);
+      if (launched) {
         cudaMemcpyAsync(tl.host, tl.dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
         return 1;
       }
@@ -384,6 +390,7 @@ void tfl_destroy(tfl_ctx* ctx) {
   if (ctx->fcache.changed) cudaFree(ctx->fcache.changed);
   if (ctx->tile.dev) cudaFree(ctx->tile.dev);
   if (ctx->tile.host) cudaFreeHost(ctx->tile.host);
+  if (ctx->tile.ev0) { cudaEventDestroy(ctx->tile.ev0); cudaEventDestroy(ctx->tile.ev1); }
   tfl_comm_destroy(ctx);
   if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1075,6 +1082,27 @@ int tfl_debug_advect_tile(tfl_ctx* ctx, int mode, int variant) {
   ctx->tile.mode = mode;
   ctx->tile.variant = variant;
   return 0;
+}
+
+// Events around the advectVel tile kernel alone (bench.py's roofline).  on: start recording; the getter
+// synchronises and returns the duration of the last recorded launch in ms (< 0 if none).
+int tfl_debug_time_advect_kernel(tfl_ctx* ctx, int on) {
+  if (!ctx) return 1;
+  DeviceGuard guard_(ctx);
+  auto& tl = ctx->tile;
+  if (on && !tl.ev0) { cudaEventCreate(&tl.ev0); cudaEventCreate(&tl.ev1); }
+  tl.timed = on != 0 && tl.ev0 && tl.ev1;
+  return 0;
+}
+float tfl_debug_last_advect_kernel_ms(tfl_ctx* ctx) {
+  if (!ctx || !ctx->tile.ev0) return -1.0f;
+  DeviceGuard guard_(ctx);
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->tile.ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->tile.ev0, ctx->tile.ev1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0f;
+  }
+  return ms;
 }
 
 int tfl_debug_cnn_use_ts(tfl_cnn* m, int on) { if (m) m->use_ts = on; return 0; }
