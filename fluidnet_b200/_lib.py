@@ -139,7 +139,7 @@ def load():
     lib.tfl_slab_sim_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tfl_slab_sim_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MConf), C.c_void_p]
     lib.tfl_slab_sim_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
-    lib.tfl_slab_sim_ipc_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p]
+    lib.tfl_slab_sim_ipc_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
     lib.tfl_slab_sim_exchange_stats.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.tfl_alloc_host.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.tfl_free_host.argtypes = [C.c_void_p, C.c_void_p]

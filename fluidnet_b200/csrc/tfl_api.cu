@@ -1698,6 +1698,10 @@ NcclApi* nccl_api() {
 
 }  // namespace
 
+// floats reserved behind the halo counters of an inbox for the all-reduce: [2 parities][world <= 64][2] doubles, then
+// [2][64] step counters
+constexpr int kSumAreaFloats = 2 * 64 * 2 * 2 + 2 * 64;
+
 struct tfl_slab_sim {
   int gnz = 0, ny = 0, nx = 0, margin = 2, halo = 6;
   int rank = 0, world = 1;
@@ -1713,6 +1717,8 @@ struct tfl_slab_sim {
   // it raises afterwards -- and the neighbours' inboxes mapped into this process.
   float* inbox = nullptr;           // cudaMalloc'ed, exported: [3 phases][2 sides][xbuf_side] floats, then 64 counters
   float* peer_inbox[2] = {nullptr, nullptr};   // lower / upper neighbour's inbox (cudaIpcOpenMemHandle)
+  std::vector<float*> all_inbox;               // every rank's inbox (own pointer at [rank]): the all-reduce's targets
+  float** all_inbox_dev = nullptr;             // the same table on the device
   unsigned int* push_done = nullptr;           // CTAs of the running push kernel that finished their stores
   bool peer_ok = false;
   unsigned int step_no = 0;
@@ -1767,7 +1773,7 @@ void tfl_slab_sim_destroy(tfl_ctx* ctx, tfl_slab_sim* s) {
   NvtxRange range_(__func__);
   if (!s) return;
   if (ctx) cudaStreamSynchronize(ctx->stream);
-  for (float* q : s->peer_inbox) if (q) cudaIpcCloseMemHandle(q);
+  for (int r = 0; r < (int)s->all_inbox.size(); r++) if (r != s->rank && s->all_inbox[r]) cudaIpcCloseMemHandle(s->all_inbox[r]);
   for (void* p : s->owned) cudaFree(p);
   for (auto& pr : s->ev) for (cudaEvent_t e : pr) if (e) cudaEventDestroy(e);
   delete s;
@@ -1826,7 +1832,7 @@ int tfl_slab_sim_create(tfl_ctx* ctx, int32_t gnz, int32_t ny, int32_t nx, int32
   bad |= cudaMalloc(&p, 4 * s->xbuf_side * sizeof(float)) != cudaSuccess;
   if (!bad) { s->owned.push_back(p); s->xbuf = (float*)p; }
   if (s->world > 1) {
-    const size_t inbox_bytes = (6 * s->xbuf_side + 64) * sizeof(float);
+    const size_t inbox_bytes = (6 * s->xbuf_side + 64 + kSumAreaFloats) * sizeof(float);
     bad |= cudaMalloc(&p, inbox_bytes) != cudaSuccess;
     if (!bad) { s->owned.push_back(p); s->inbox = (float*)p; bad |= cudaMemset(p, 0, inbox_bytes) != cudaSuccess; }
     bad |= cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess;
@@ -1969,6 +1975,57 @@ __global__ void k_slab_pull(SlabPack d, const float* buf_lo, const float* buf_hi
   }
 }
 
+// All-reduce of the two partial sums over peer memory: every rank stores its pair into slot [parity][rank] of every
+// rank's inbox and raises that rank's counter [parity][rank]; then waits for all counters of its own inbox and adds
+// the pairs in rank order (the same order on every rank: identical results everywhere, independent of timing).
+// Slots alternate with the step's parity: a rank that is still reading step s cannot be overwritten by step s + 1.
+__device__ __forceinline__ double* sum_slot(float* inbox, size_t xbuf_side, int parity, int r) {
+  return reinterpret_cast<double*>(inbox + 6 * xbuf_side + 64) + ((size_t)parity * 64 + r) * 2;
+}
+__device__ __forceinline__ unsigned int* sum_flag(float* inbox, size_t xbuf_side, int parity, int r) {
+  return reinterpret_cast<unsigned int*>(inbox + 6 * xbuf_side + 64 + 2 * 64 * 2 * 2) + parity * 64 + r;
+}
+__global__ void k_sum_push(const double* __restrict__ mine, float* const* __restrict__ inboxes, size_t xbuf_side, int rank,
+                           int world, unsigned int step) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  const int parity = step & 1;
+  double* slot = sum_slot(inboxes[t], xbuf_side, parity, rank);
+  slot[0] = mine[0];
+  slot[1] = mine[1];
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sum_flag(inboxes[t], xbuf_side, parity, rank)), "r"(step) : "memory");
+}
+__global__ void k_sum_pull(double* __restrict__ out, float* inbox, size_t xbuf_side, int world, unsigned int step,
+                           unsigned long long* faults) {
+  __shared__ int ok;
+  const int t = threadIdx.x, parity = step & 1;
+  if (t == 0) ok = 1;
+  __syncthreads();
+  if (t < world) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sum_flag(inbox, xbuf_side, parity, t)) : "memory");
+      if ((int)(v - step) >= 0) break;
+      if (clock64() - t0 > 4000000000LL) { ok = 0; break; }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    if (!ok) { if (faults) atomicAdd(faults, 1ULL); return; }
+    double s0 = 0.0, s1 = 0.0;
+    for (int r = 0; r < world; r++) {
+      const volatile double* slot = sum_slot(inbox, xbuf_side, parity, r);
+      s0 += slot[0];
+      s1 += slot[1];
+    }
+    out[0] = s0;
+    out[1] = s1;
+  }
+}
+
 // Refresh `width` ghost planes on both sides of the listed fields from the neighbours' owned planes.
 int slab_exchange(tfl_ctx* ctx, tfl_slab_sim* s, std::initializer_list<const tfl_grid*> fields, int width, int phase) {
   TFL_CUDA(ctx, cudaEventRecord(s->ev[phase][0], ctx->stream));
@@ -2098,7 +2155,13 @@ int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* s, const tfl_mconf* mc, tfl_cn
     if (tfl_cnn_stats(ctx, &st.U, &st.flags, &u1, s->sums)) return 1;
   }
   TFL_CUDA(ctx, cudaEventRecord(s->ev[3][0], ctx->stream));
-  if (s->world > 1 && ctx->comm) TFL_NCCL(ctx, nccl_api()->AllReduce(s->sums, s->sums, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  if (s->world > 1 && s->peer_ok && s->all_inbox_dev) {
+    k_sum_push<<<1, 64, 0, ctx->stream>>>(s->sums, s->all_inbox_dev, s->xbuf_side, s->rank, s->world, s->step_no);
+    k_sum_pull<<<1, 64, 0, ctx->stream>>>(s->sums, s->inbox, s->xbuf_side, s->world, s->step_no, ctx->counters);
+    ctx->launches += 2;
+  } else if (s->world > 1 && ctx->comm) {
+    TFL_NCCL(ctx, nccl_api()->AllReduce(s->sums, s->sums, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  }
   TFL_CUDA(ctx, cudaEventRecord(s->ev[3][1], ctx->stream));
   {
     SlabScope scope(ctx, s, s->own_lo, s->own_hi);
@@ -2123,35 +2186,49 @@ int tfl_slab_sim_ipc_export(tfl_ctx* ctx, tfl_slab_sim* s, char* handle_out) {
   return 0;
 }
 
-// ... and map the neighbours' (rank - 1: lo_handle, rank + 1: hi_handle; NULL where there is none).  From then on
-// tfl_slab_sim_step exchanges halos with push / pull kernels over NVLink instead of NCCL send / recv.  Every rank
-// must connect before any rank steps (the host application's barrier).
-int tfl_slab_sim_ipc_connect(tfl_ctx* ctx, tfl_slab_sim* s, const char* lo_handle, const char* hi_handle) {
+// ... and map every rank's (handles: world x TFL_IPC_HANDLE_BYTES in rank order; NULL switches back to NCCL).
+// From then on tfl_slab_sim_step exchanges halos with push / pull kernels over NVLink instead of NCCL send / recv
+// and reduces the two sums through the same inboxes.  Every rank must connect before any rank steps (the host
+// application's barrier).
+int tfl_slab_sim_ipc_connect(tfl_ctx* ctx, tfl_slab_sim* s, const char* handles) {
   DeviceGuard guard_(ctx);
   NvtxRange range_(__func__);
   if (!s || !s->inbox) return fail(ctx, "slab_sim_ipc_connect: nil argument");
-  if (!lo_handle && !hi_handle) {                 // back to NCCL (e.g. another rank could not map its neighbours)
-    TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (float*& m : s->peer_inbox) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+  auto drop = [&]() {
+    for (int r = 0; r < (int)s->all_inbox.size(); r++)
+      if (r != s->rank && s->all_inbox[r]) cudaIpcCloseMemHandle(s->all_inbox[r]);
+    s->all_inbox.clear();
+    s->peer_inbox[0] = s->peer_inbox[1] = nullptr;
     s->peer_ok = false;
-    return 0;
-  }
-  const char* hs[2] = {lo_handle, hi_handle};
-  const bool need[2] = {s->rank > 0, s->rank < s->world - 1};
-  for (int i = 0; i < 2; i++) {
-    if (!need[i]) continue;
-    if (!hs[i]) return fail(ctx, "slab_sim_ipc_connect: missing neighbour handle");
+  };
+  TFL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  drop();
+  if (!handles) return 0;                          // back to NCCL (e.g. another rank could not map its peers)
+  if (s->world > 64) return fail(ctx, "slab_sim_ipc_connect: more than 64 ranks");
+  s->all_inbox.assign(s->world, nullptr);
+  s->all_inbox[s->rank] = s->inbox;
+  for (int r = 0; r < s->world; r++) {
+    if (r == s->rank) continue;
     cudaIpcMemHandle_t h;
-    memcpy(&h, hs[i], sizeof(h));
+    memcpy(&h, handles + (size_t)r * TFL_IPC_HANDLE_BYTES, sizeof(h));
     void* q = nullptr;
     const cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      for (float*& m : s->peer_inbox) if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
-      return fail(ctx, "slab_sim_ipc_connect: cudaIpcOpenMemHandle: %s (halos stay on NCCL)", cudaGetErrorString(e));
+      drop();
+      return fail(ctx, "slab_sim_ipc_connect: cudaIpcOpenMemHandle(rank %d): %s (the exchanges stay on NCCL)", r, cudaGetErrorString(e));
     }
-    s->peer_inbox[i] = (float*)q;
+    s->all_inbox[r] = (float*)q;
   }
+  if (!s->all_inbox_dev) {
+    void* p = nullptr;
+    TFL_CUDA(ctx, cudaMalloc(&p, 64 * sizeof(float*)));
+    s->owned.push_back(p);
+    s->all_inbox_dev = (float**)p;
+  }
+  TFL_CUDA(ctx, cudaMemcpy(s->all_inbox_dev, s->all_inbox.data(), s->world * sizeof(float*), cudaMemcpyHostToDevice));
+  if (s->rank > 0) s->peer_inbox[0] = s->all_inbox[s->rank - 1];
+  if (s->rank < s->world - 1) s->peer_inbox[1] = s->all_inbox[s->rank + 1];
   s->peer_ok = true;
   return 0;
 }

@@ -91,7 +91,7 @@ int tfl_slab_sim_upload(tfl_ctx*, tfl_slab_sim* sim, const float* p, const float
 int tfl_slab_sim_download(tfl_ctx*, tfl_slab_sim* sim, float* p, float* U, float* density);
 int tfl_slab_sim_step(tfl_ctx*, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
 int tfl_slab_sim_ipc_export(tfl_ctx*, tfl_slab_sim* sim, char* handle_out);
-int tfl_slab_sim_ipc_connect(tfl_ctx*, tfl_slab_sim* sim, const char* lo_handle, const char* hi_handle);
+int tfl_slab_sim_ipc_connect(tfl_ctx*, tfl_slab_sim* sim, const char* handles);
 ]]
 
 local lib = ffi.load('tfl')          -- libtfl.so on the library path
@@ -315,7 +315,9 @@ function tfluids.slabIpcHandle(sim)                 -- 64 bytes for the neighbou
   check(lib.tfl_slab_sim_ipc_export(ctx, sim, h))
   return ffi.string(h, 64)
 end
-function tfluids.slabIpcConnect(sim, loHandle, hiHandle) check(lib.tfl_slab_sim_ipc_connect(ctx, sim, loHandle, hiHandle)) end
+function tfluids.slabIpcConnect(sim, allHandles)     -- the 64-byte handles of every rank, concatenated in rank order
+  check(lib.tfl_slab_sim_ipc_connect(ctx, sim, allHandles))
+end
 function tfluids.slabUpload(sim, p, U, density) check(lib.tfl_slab_sim_upload(ctx, sim, p, U, density)) end
 function tfluids.slabStep(sim, cmconf, model) check(lib.tfl_slab_sim_step(ctx, sim, cmconf, model)) end
 function tfluids.slabDownload(sim, p, U, density) check(lib.tfl_slab_sim_download(ctx, sim, p, U, density)) end

@@ -260,9 +260,7 @@ class NativeSlabSimulator:
             handles = [None] * self.world
             dist.all_gather_object(handles, buf.raw if ok else None, group=group)
             if all(h is not None for h in handles):
-                lo = handles[self.rank - 1] if self.rank > 0 else None
-                hi = handles[self.rank + 1] if self.rank < self.world - 1 else None
-                ok = lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, lo, hi) == 0
+                ok = lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, b"".join(handles)) == 0
             else:
                 ok = False
             flags_ok = [None] * self.world
@@ -270,7 +268,7 @@ class NativeSlabSimulator:
             if all(flags_ok):
                 self.halo_transport = "peer memory (CUDA IPC over NVLink)"
             elif ok:                                          # every rank must use the same transport
-                self.ctx.check(lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, None, None))
+                self.ctx.check(lib.tfl_slab_sim_ipc_connect(self.ctx.h, self.h, None))
 
     def step(self):
         self.ctx.use_current_stream()

@@ -303,15 +303,16 @@ int tfl_slab_sim_download(tfl_ctx* ctx, tfl_slab_sim* sim, float* p, float* U, f
  * A trace that leaves the local slab (margin too small) raises tfl_trace_faults. */
 int tfl_slab_sim_step(tfl_ctx* ctx, tfl_slab_sim* sim, const tfl_mconf* mconf, tfl_cnn* cnn);
 int tfl_slab_sim_exchange_stats(tfl_ctx* ctx, tfl_slab_sim* sim, float ms[4], int64_t bytes[3]);
-/* Halo exchange over peer memory instead of NCCL: every rank exports its inbox as a CUDA IPC handle, the host
- * application hands each rank the handles of ranks r - 1 and r + 1 (NULL at the ends), and after
- * tfl_slab_sim_ipc_connect on EVERY rank (host-side barrier before the first step) an exchange is one kernel that
- * writes the boundary planes straight into the neighbours' memory over NVLink and raises their step counters, and
- * one kernel that waits for this rank's counters and scatters its inbox into the ghost planes.  Optional: without
- * it the exchanges use ncclSend / ncclRecv.  The 2-double all-reduce stays on NCCL. */
+/* The exchanges over peer memory instead of NCCL: every rank exports its inbox as a CUDA IPC handle, the host
+ * application gives every rank the handles of ALL ranks (world x TFL_IPC_HANDLE_BYTES, rank order), and after
+ * tfl_slab_sim_ipc_connect on EVERY rank (host-side barrier before the first step) a halo exchange is one kernel
+ * that writes the boundary planes straight into the neighbours' memory over NVLink and raises their step counters,
+ * and one kernel that waits for this rank's counters and scatters its inbox into the ghost planes; the two sums are
+ * reduced the same way (every rank stores its pair into every inbox and adds the pairs in rank order).  Optional:
+ * without it -- or after tfl_slab_sim_ipc_connect(ctx, sim, NULL) -- the exchanges use NCCL. */
 #define TFL_IPC_HANDLE_BYTES 64
 int tfl_slab_sim_ipc_export(tfl_ctx* ctx, tfl_slab_sim* sim, char* handle_out /* TFL_IPC_HANDLE_BYTES */);
-int tfl_slab_sim_ipc_connect(tfl_ctx* ctx, tfl_slab_sim* sim, const char* lo_handle, const char* hi_handle);
+int tfl_slab_sim_ipc_connect(tfl_ctx* ctx, tfl_slab_sim* sim, const char* handles);
 #ifdef __cplusplus
 }
 #endif
