@@ -163,14 +163,16 @@ static bool conv_launch(const float* in, float* out, const float* w, const float
   const size_t smem = sizeof(float) * cin * KZ * KS * KS * COUT;
   if (smem > 200 * 1024) return false;             // weights do not fit shared memory: generic kernel
   if (smem > 48 * 1024) {
-    static size_t allowed = 0;                     // per instantiation
-    if (smem > allowed) {
+    static size_t allowed[64];                     // per instantiation and device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > allowed[dev & 63]) {
       if (cudaFuncSetAttribute(k_conv_direct<COUT, KS, IS3D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return false;
       }
-      allowed = smem;
+      allowed[dev & 63] = smem;
     }
   }
   k_conv_direct<COUT, KS, IS3D><<<grid, block, smem, st>>>(in, out, w, b, cin, act, g);

@@ -355,10 +355,12 @@ void launch_one(const float4* in, float4* out, float* p_net, const float* wB, co
   constexpr int NB = SPLIT ? 48 : 32;
   const size_t smem = (size_t)(SPLIT ? 4 : 2) * T::PLANE_BYTES + kGroups * 2 * NB * 16 + 64 + 4 * 96;
   auto kern = k_conv3_tc<IN_PLANES, FINAL, SPLIT>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;       // per device (function attributes are)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1ULL)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    configured |= 1ULL << (dev & 63);
   }
   const int ntz = (g.z_hi - g.z_lo + T::TZ - 1) / T::TZ;       // output planes [z_lo, z_hi)
   ConvTcGeo gg = g;

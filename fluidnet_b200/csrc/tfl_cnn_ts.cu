@@ -358,10 +358,12 @@ void launch_ts(const float4* in, float4* out, float* p_net, const float* wB, con
                const float* tail, const ConvTcGeo& g, cudaStream_t st) {
   const size_t smem = (size_t)kGroups * kBGroupBytes + kNumBars * 8 + 16 + 96 * 4 + 2 * kNDBuf * 64 * 4 + 64 + 64;
   auto kern = k_conv3_ts<IN_PLANES, FINAL>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;       // per device (function attributes are)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1ULL)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    configured |= 1ULL << (dev & 63);
   }
   const int nty = (g.ny + kTY - 1) / kTY;
   // one wave of persistent-style CTAs: as many z chunks as fit 148 SMs

@@ -1163,15 +1163,18 @@ bool launch_jacobi_sweeps(const unsigned char* mask, const float* div, float* pa
       g.n * g.nb > (3LL << 20) || sweeps < 2)
     return false;
   const int smem = kJG * (kJZ * (kJY + 2) * 32 + kJZ * kJY * 32) * (int)sizeof(float4);
-  static int capacity = -1;          // resident CTAs of this kernel on the device
-  if (capacity < 0) {
-    int dev = 0, sms = 0, per_sm = 0, coop = 0;
-    cudaGetDevice(&dev);
+  static int capacities[64];         // resident CTAs of this kernel, per device (0: not asked yet, -1: cannot)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& capacity = capacities[dev & 63];
+  if (capacity == 0) {
+    int sms = 0, per_sm = 0, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    capacity = 0;
+    capacity = -1;
     if (coop && cudaFuncSetAttribute(k_jacobi_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_resident, 256 * kJG, smem) == cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jacobi_resident, 256 * kJG, smem) == cudaSuccess &&
+        sms * per_sm > 0)
       capacity = sms * per_sm;
     cudaGetLastError();
   }
