@@ -373,9 +373,14 @@ def main():
             sampler.start()
         total_ms, launches = timed_steps(gb, args.steps, max(args.warmup, 3))
         lg0 = ctx.launch_count()
-        graph_ms = timed_graph_steps(gb, args.steps)
-        # kernels inside the timed graph region: the 2 untimed warm-up replays are subtracted
-        graph_launches = (ctx.launch_count() - lg0) * args.steps // (args.steps + 2)
+        graph_error = None
+        try:
+            graph_ms = timed_graph_steps(gb, args.steps)
+            # kernels inside the timed graph region: the 2 untimed warm-up replays are subtracted
+            graph_launches = (ctx.launch_count() - lg0) * args.steps // (args.steps + 2)
+        except Exception as e:                      # a box that cannot capture: the kernel-by-kernel number is the headline
+            graph_error = "%s: %s" % (type(e).__name__, e)
+            graph_ms, graph_launches = total_ms, launches
         # trace-length regime of the timed steps (the advection cost is data dependent)
         max_u_dt = float(gb["UDiv"].abs().max().item()) * mconf["dt"]
         if world > 1:
@@ -519,7 +524,10 @@ def main():
     if not args.no_slab:
         del gb
         torch.cuda.empty_cache()
-        slab = measure_slab(args.slab_grid, max(3, min(args.steps, 10)), 3, world, rank, local)
+        try:
+            slab = measure_slab(args.slab_grid, max(3, min(args.steps, 10)), 3, world, rank, local)
+        except Exception as e:                      # the sub-record must not take the headline down with it
+            slab = {"error": "%s: %s" % (type(e).__name__, e)} if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -562,7 +570,8 @@ def main():
                    "l2": "256 MB buffer written between timed steps (L2 flush)",
                    "velocity": "band-limited (4 Fourier modes per component), +-2 cells/s at step 0",
                    "max_u_dt_cells_at_end": max_u_dt},
-        "launch_mode": "CUDA graph replay (tfl_step_graph_launch), one launch per step",
+        "launch_mode": ("CUDA graph replay (tfl_step_graph_launch), one launch per step" if graph_error is None else
+                        "kernel by kernel (graph capture failed: %s)" % graph_error),
         "ungraphed": {"value": world * 1000.0 / ms_direct, "unit": "steps/s", "ms_per_step": ms_direct,
                       "what": "the same step through tfl_simulate_step, kernel by kernel"},
         "variant_random_velocity": variant,

@@ -34,3 +34,14 @@ def test_reference_arm_json_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_roofline_traffic_is_read_from_the_tracked_ncu_table():
+    """bench.py's roofline.traffic comes from profiles/r02_advect_ncu_raw.csv (the ncu --set full capture of the
+    current advection kernels), never from a literal: the parser finds the kernel and gives DRAM bytes per launch."""
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, src = bench.ncu_traffic([r"k_advect_vel_tile"])
+    assert src == os.path.join("profiles", "r02_advect_ncu_raw.csv")
+    assert 5e6 < traffic < 2e8, traffic           # bytes per launch at 128^3 (algorithmic: 58.7 MB)
+    assert bench.ncu_traffic([r"no_such_kernel"]) == (None, None)
