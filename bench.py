@@ -492,8 +492,9 @@ def main():
                 stream.synchronize()
                 ms_j = a.elapsed_time(b)
                 ach = 16.0 * nj ** 3 * 100 / (ms_j * 1e-3) / 1e9
-                extra.append({"kernel": "Jacobi x100 (k_jacobi_mask + 100 x %s), %d^3"
-                                        % ("k_jacobi_march" if nj >= 256 else "k_jacobi_iter4", nj),
+                extra.append({"kernel": "Jacobi x100 (k_jacobi_mask + %s), %d^3"
+                                        % ("100 x k_jacobi_march" if nj >= 256 else
+                                           "k_jacobi_resident: 99 sweeps in one cooperative launch + 1 x k_jacobi_iter4", nj),
                               "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                               "ms": ms_j, "algorithmic_bytes_per_voxel_iter": 16})
                 if nj == 128:
