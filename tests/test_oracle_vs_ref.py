@@ -92,3 +92,44 @@ def test_line_trace_random(orc, ref):
         assert ha == hb and bits_equal(pa, pb), (pos, delta, pa, pb)
         n += 1
     assert n > 2000
+
+
+TILE_GRIDS = [((40, 24, 20), True, False), ((36, 20, 12), True, True), ((64, 16, 5), False, False)]
+
+
+@pytest.mark.parametrize("dims,geom,exotic", TILE_GRIDS, ids=["40x24x20_geom", "36x20x12_exotic", "64x16x5_empty"])
+@pytest.mark.parametrize("amp", [2.0, 4.7, 5.2, 8.0, 14.5, 25.0])
+def test_maccormack_ours_in_the_tile_kernels_regimes(orc, ref, dims, geom, exotic, amp):
+    """The inputs of tests/test_gpu_advect_tile.py (the GPU's shared-memory tile kernels are compared with the
+    restatement there), plus amplitudes right at the trace lengths where the GPU dispatcher switches code paths
+    (0.47 / 0.52 cell: halo 1 -> 2; 1.45: halo 2 -> general): here the restatement itself is pinned on the
+    reference's compiled CPU code for exactly these fields, single batch element as the tile kernels take."""
+    from fluidnet_b200 import synth
+    nx, ny, nz = dims
+    flags = synth.make_flags(nx, ny, nz, True, nb=1, geometry=geom, exotic=exotic)
+    U = synth.make_velocity(flags, True, amp=amp)
+    orc.setWallBcsForward(U, flags)
+    a = orc.advectVel(0.1, U, flags, "maccormackOurs", 0.6)
+    b = ref.advectVel(0.1, U, flags, "maccormackOurs", 0.6)
+    assert bits_equal(a, b), "advectVel " + describe_diff(a, b)
+    rho = synth.make_density(flags)
+    rho[np.random.RandomState(3).rand(*rho.shape) < 0.3] = 0.0
+    for outside in (False, True):
+        a = orc.advectScalar(0.1, rho, U, flags, "maccormackOurs", outside, 0.6)
+        b = ref.advectScalar(0.1, rho, U, flags, "maccormackOurs", outside, 0.6)
+        assert bits_equal(a, b), "advectScalar(outside=%s) %s" % (outside, describe_diff(a, b))
+
+
+def test_signed_zero_fields_match_the_reference(orc, ref):
+    """+0 / -0 mixtures (the clamp's compare-and-keep order decides the sign of a zero bound): the input of
+    test_gpu_advect_tile.py::test_zero_bounds_keep_their_sign, restatement vs compiled reference."""
+    from fluidnet_b200 import synth
+    flags = synth.make_flags(40, 24, 20, True, nb=1, geometry=True)
+    U = synth.make_smooth_velocity(flags, True, amp=3.0)
+    rng = np.random.RandomState(5)
+    U[rng.rand(*U.shape) < 0.35] = 0.0
+    U[rng.rand(*U.shape) < 0.2] = -0.0
+    orc.setWallBcsForward(U, flags)
+    a = orc.advectVel(0.1, U, flags, "maccormackOurs", 0.6)
+    b = ref.advectVel(0.1, U, flags, "maccormackOurs", 0.6)
+    assert bits_equal(a, b), describe_diff(a, b)
