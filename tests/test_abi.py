@@ -94,3 +94,23 @@ def test_lua_shim_is_consistent_with_the_header():
                  "volumetricUpSamplingNearestForward", "volumetricUpSamplingNearestBackward",
                  "velocityDivergenceBackward", "velocityUpdateBackward"):
         assert name in defined, name
+
+
+def test_header_is_plain_c_and_a_c_host_links_against_the_abi(tmp_path):
+    """include/tfl.h must be consumable from C (LuaJIT's ffi.cdef, cgo, a C host): examples/c_host.c -- one step
+    through the ABI from plain C99, the library dlopen'ed -- compiles, and without a GPU fails cleanly in
+    tfl_create (exit code 1, a message, no crash)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "examples", "c_host.c")
+    exe = str(tmp_path / "c_host")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), src, "-o", exe, "-ldl"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, os.path.join(root, "fluidnet_b200", "libtfl.so")], capture_output=True, text=True, timeout=120)
+    assert r.returncode in (0, 1), (r.returncode, r.stderr)
+    if r.returncode == 1:
+        assert "tfl_create failed" in r.stderr or "libtfl:" in r.stderr
+    else:
+        assert "step done" in r.stdout
